@@ -1,0 +1,455 @@
+// K5 engine 1: convolution as implicit GEMM on the 5th-generation tensor cores.
+//
+//   D[pixels, Cout] (fp32, TMEM)  +=  A[pixels, (tap, cin)] (fp16, smem)  x  B[Cout, (tap, cin)]^T (fp16, smem)
+//
+// * A is never materialised: for every filter tap the TMA engine loads the
+//   shifted (tn x th x tw) pixel box of the NHWC activation tensor -- a 4-D
+//   tiled tensor map (C, W, H, N) whose out-of-bounds zero fill IS the
+//   convolution's zero padding; stride-2 convolutions use the map's element
+//   strides.  The box lands in shared memory as 128-byte (64-channel) or
+//   64-byte (32-channel) rows in the hardware swizzle, which is exactly the
+//   K-major canonical layout tcgen05.mma reads through a shared-memory
+//   descriptor.  B (weights, [tap][cout][cin]) comes through a 2-D map.
+// * One CTA = 128*m_tiles output pixels x n_tile output channels.  Warp 0
+//   produces (TMA + mbarrier expect_tx), lane 0 of warp 1 issues
+//   tcgen05.mma.cta_group::1.kind::f16 (M=128, N=n_tile, K=16) into TMEM and
+//   commits to the stage's "empty" barrier, warps 2..5 are the epilogue:
+//   tcgen05.ld 32x32b -> +bias (+residual) -> ReLU -> fp16 -> NHWC store, with
+//   the fuse layers' nearest upsample folded into the store.
+// * Several CTAs share an SM (small stages, <= 512 TMEM columns in total), so
+//   one CTA's epilogue overlaps another's main loop.
+//
+// Bound: tensor pipe (2*pixels*Cout*Cin*k*k flop per launch); see DESIGN.md.
+#include "hrnet.cuh"
+#include <cstdlib>
+#include <cstring>
+
+// ---------------------------------------------------------------------------
+// driver entry point for tensor-map encoding (no link-time libcuda dependency)
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+struct ConvParams {
+    int P, Ho, Wo, Cout, up, relu;
+    int tn, th, tw, m_tiles, n_tile;
+    int chunk, n_chunks, ksz, stride;
+    int tiles_w, tiles_h;
+    int stages;
+    uint32_t a_stage_bytes, b_stage_bytes, tx_bytes;
+    uint32_t row_bytes;          // 64 or 128
+    uint32_t tmem_cols;
+    uint32_t idesc;
+    const float* bias;
+    const __half* res;
+    __half* out;
+};
+
+struct UmmaPlan {
+    CUtensorMap tmA, tmB;
+    ConvParams prm;
+    size_t smem_bytes;
+    int n_splits;
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    // try_wait suspends in hardware for a bounded time; a pipeline that has not
+    // advanced for ~2 s is a bug (wrong expect_tx byte count, bad tensor map):
+    // trap instead of hanging the GPU.
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, hardware swizzle (SM100 format):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4
+//   [46,48) version=1 | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8u * row_bytes) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;
+    return d;
+}
+
+constexpr int kThreads = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
+
+__global__ void __launch_bounds__(kThreads)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [A stages][B stages] (1024-aligned), then barriers
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_base = smem_base;
+    const uint32_t b_base = a_base + p.stages * p.a_stage_bytes;
+    const uint32_t bar_base = b_base + p.stages * p.b_stage_bytes;      // 8-byte aligned
+    const uint32_t full_bar = bar_base;                                 // stages x 8 B
+    const uint32_t empty_bar = bar_base + 8u * p.stages;
+    const uint32_t tmem_full_bar = bar_base + 16u * p.stages;
+    const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int taps = p.ksz * p.ksz;
+    const int k_iters = taps * p.n_chunks;
+
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+    const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+    const int n0 = t * p.tn, h0 = tile_h * p.th, w0 = tile_w * p.tw;
+    const int n_off = blockIdx.y * p.n_tile;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full_bar + 8u * s, 1);
+            mbar_init(empty_bar + 8u * s, 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const int pad = p.ksz / 2;
+            int it = 0;
+            for (int tap = 0; tap < taps; ++tap) {
+                const int dy = tap / p.ksz - pad, dx = tap % p.ksz - pad;
+                for (int cc = 0; cc < p.n_chunks; ++cc, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(empty_bar + 8u * s, ph ^ 1u);
+                    mbar_expect_tx(full_bar + 8u * s, p.tx_bytes);
+                    tma_load_4d(a_base + s * p.a_stage_bytes, &tmA, full_bar + 8u * s,
+                                cc * p.chunk, w0 * p.stride + dx, h0 * p.stride + dy, n0);
+                    tma_load_2d(b_base + s * p.b_stage_bytes, &tmB, full_bar + 8u * s,
+                                cc * p.chunk, tap * p.Cout + n_off);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const int ksteps = p.chunk / 16;
+            for (int it = 0; it < k_iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(full_bar + 8u * s, ph);
+                tc_fence_after();
+                const uint32_t a_s = a_base + s * p.a_stage_bytes, b_s = b_base + s * p.b_stage_bytes;
+                for (int mt = 0; mt < p.m_tiles; ++mt) {
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t ad = make_desc(a_s + mt * 128u * p.row_bytes + k * 32u, p.row_bytes);
+                        const uint64_t bd = make_desc(b_s + k * 32u, p.row_bytes);
+                        umma_f16(tmem_base + mt * p.n_tile, ad, bd, p.idesc, (it | k) ? 1u : 0u);
+                    }
+                }
+                umma_commit(empty_bar + 8u * s);          // frees the stage when these MMAs retire
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int grp = warp & 3;                          // TMEM lane group this warp may read
+        const int Hout = p.Ho * p.up, Wout = p.Wo * p.up;
+        for (int mt = 0; mt < p.m_tiles; ++mt) {
+            const int R = mt * 128 + grp * 32 + lane;
+            const int ww = R % p.tw, hh = (R / p.tw) % p.th, nn = R / (p.tw * p.th);
+            const int n = n0 + nn, ho = h0 + hh, wo = w0 + ww;
+            const bool valid = n < p.P;
+            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + ((uint32_t)(grp * 32) << 16) + (uint32_t)(mt * p.n_tile + c0), r);
+                tmem_ld_wait();
+                if (!valid) continue;
+                float v[16];
+                const float4* bz = reinterpret_cast<const float4*>(p.bias + n_off + c0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b4 = __ldg(bz + q);
+                    v[4 * q] = __uint_as_float(r[4 * q]) + b4.x;
+                    v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+                    v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
+                    v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+                }
+                for (int uy = 0; uy < p.up; ++uy)
+                    for (int ux = 0; ux < p.up; ++ux) {
+                        const size_t o = ((((size_t)n * Hout + ho * p.up + uy) * Wout) + wo * p.up + ux) * p.Cout + n_off + c0;
+                        float x[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) x[q] = v[q];
+                        if (p.res) {
+                            const uint4 q0 = *reinterpret_cast<const uint4*>(p.res + o);
+                            const uint4 q1 = *reinterpret_cast<const uint4*>(p.res + o + 8);
+                            const __half2* h0p = reinterpret_cast<const __half2*>(&q0);
+                            const __half2* h1p = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 f0 = __half22float2(h0p[q]), f1 = __half22float2(h1p[q]);
+                                x[2 * q] += f0.x; x[2 * q + 1] += f0.y;
+                                x[8 + 2 * q] += f1.x; x[8 + 2 * q + 1] += f1.y;
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) x[q] = fmaxf(x[q], 0.f);
+                        }
+                        __align__(16) __half2 pk[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) pk[q] = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+                        *reinterpret_cast<uint4*>(p.out + o) = *reinterpret_cast<const uint4*>(&pk[0]);
+                        *reinterpret_cast<uint4*>(p.out + o + 8) = *reinterpret_cast<const uint4*>(&pk[4]);
+                    }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+bool pick_tile(int Ho, int Wo, int m_tiles, int* tn, int* th, int* tw) {
+    const int rows = 128 * m_tiles;
+    for (int n = 1; n <= 32; n *= 2) {
+        if (rows % n) continue;
+        const int per = rows / n;
+        for (int w = Wo < per ? Wo : per; w >= 1; --w) {
+            if (Wo % w || per % w) continue;
+            const int h = per / w;
+            if (h > Ho || Ho % h) continue;
+            if (w > 256 || h > 256) continue;
+            *tn = n; *th = h; *tw = w;
+            return true;
+        }
+    }
+    return false;
+}
+
+int stride_mode() {
+    // how a tiled tensor map with elementStrides = s sizes its box:
+    //   1 (default): boxDim counts SOURCE elements spanned, ceil(box/s) are written
+    //   2          : boxDim counts elements written
+    //   0          : stride-2 convolutions stay on the SIMT engine
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("HBP_TMA_STRIDE_MODE");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
+}
+
+}  // namespace
+
+bool umma_supported(const HrnetModel& m, const HOp& op) {
+    if (op.kind != OP_CONV) return false;
+    if (!(op.k == 1 || op.k == 3) || !(op.stride == 1 || op.stride == 2)) return false;
+    if (op.stride == 2 && stride_mode() == 0) return false;
+    if (!(op.cin == 32 || op.cin % 64 == 0)) return false;
+    if (op.cout % 16 != 0) return false;
+    const HTensor& ti = m.tensors[op.in];
+    int tn, th, tw;
+    if (!pick_tile(ti.h / op.stride, ti.w / op.stride, 1, &tn, &th, &tw)) return false;
+    return get_encode() != nullptr;
+}
+
+void umma_plan_destroy(UmmaPlan* p) { delete p; }
+
+int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPlan** out) {
+    const HOp& op = m.ops[op_index];
+    const HTensor& ti = m.tensors[op.in];
+    const int Ho = ti.h / op.stride, Wo = ti.w / op.stride;
+    UmmaPlan* pl = new UmmaPlan();
+    ConvParams& p = pl->prm;
+    memset(&p, 0, sizeof(p));
+    // N tile: largest divisor of Cout that is a multiple of 16 and <= 256
+    int n_tile = 0;
+    for (int c = op.cout < 256 ? op.cout : 256; c >= 16; c -= 16)
+        if (op.cout % c == 0) { n_tile = c; break; }
+    if (!n_tile) { delete pl; hbp_set_error("no N tile for Cout=%d", op.cout); return HBP_ERR_INVALID; }
+    // M tiles per CTA: 2 when that still leaves >= 2 CTAs per SM and TMEM fits
+    int m_tiles = 2, tn = 0, th = 0, tw = 0;
+    {
+        bool ok2 = pick_tile(Ho, Wo, 2, &tn, &th, &tw) && 2 * n_tile <= 512;
+        if (ok2) {
+            const long ctas = (long)((capP + tn - 1) / tn) * (Ho / th) * (Wo / tw) * (op.cout / n_tile);
+            if (ctas < 2L * ctx->sm_count) ok2 = false;
+        }
+        if (!ok2) { m_tiles = 1; pick_tile(Ho, Wo, 1, &tn, &th, &tw); }
+    }
+    // too few CTAs: split N further (down to 32)
+    {
+        long ctas = (long)((capP + tn - 1) / tn) * (Ho / th) * (Wo / tw) * (op.cout / n_tile);
+        while (ctas < ctx->sm_count && n_tile % 32 == 0 && n_tile > 32) { n_tile /= 2; ctas *= 2; }
+    }
+    p.Ho = Ho; p.Wo = Wo; p.Cout = op.cout; p.up = op.up; p.relu = op.relu;
+    p.tn = tn; p.th = th; p.tw = tw; p.m_tiles = m_tiles; p.n_tile = n_tile;
+    p.chunk = op.cin == 32 ? 32 : 64;
+    p.n_chunks = op.cin / p.chunk;
+    p.ksz = op.k; p.stride = op.stride;
+    p.tiles_w = Wo / tw; p.tiles_h = Ho / th;
+    p.row_bytes = p.chunk * 2;
+    p.a_stage_bytes = 128u * m_tiles * p.row_bytes;
+    p.b_stage_bytes = ((uint32_t)n_tile * p.row_bytes + 1023u) & ~1023u;
+    p.tx_bytes = p.a_stage_bytes + (uint32_t)n_tile * p.row_bytes;
+    const uint32_t stage = p.a_stage_bytes + p.b_stage_bytes;
+    const int k_iters = op.k * op.k * p.n_chunks;
+    const uint32_t budget = stage * 4 <= 96 * 1024 ? 96 * 1024 : 200 * 1024;
+    int stages = budget / stage;
+    if (stages > 8) stages = 8;
+    if (stages > k_iters) stages = k_iters;
+    if (stages < 1) { delete pl; hbp_set_error("stage too large"); return HBP_ERR_INVALID; }
+    p.stages = stages;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(m_tiles * n_tile)) cols *= 2;
+    p.tmem_cols = cols;
+    // instruction descriptor: D=F32 (bits 4-5 = 1), A=B=F16 (0), K-major both, N>>3 at 17, M>>4 at 24
+    p.idesc = (1u << 4) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    p.bias = m.d_bias + op.b_off;
+    p.res = op.res >= 0 ? m.bufs[m.tensors[op.res].buf] : nullptr;
+    p.out = m.bufs[m.tensors[op.out].buf];
+    pl->smem_bytes = (size_t)stages * stage + 16 * stages + 32 + 1024;
+    pl->n_splits = op.cout / n_tile;
+
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { delete pl; hbp_set_error("cuTensorMapEncodeTiled unavailable"); return HBP_ERR_CUDA; }
+    const CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    {
+        cuuint64_t gdim[4] = {(cuuint64_t)ti.c, (cuuint64_t)ti.w, (cuuint64_t)ti.h, (cuuint64_t)capP};
+        cuuint64_t gstr[3] = {(cuuint64_t)ti.c * 2, (cuuint64_t)ti.w * ti.c * 2, (cuuint64_t)ti.h * ti.w * ti.c * 2};
+        const int s = op.stride;
+        const int bw = (s == 2 && stride_mode() == 1) ? tw * s : tw;
+        const int bh = (s == 2 && stride_mode() == 1) ? th * s : th;
+        cuuint32_t box[4] = {(cuuint32_t)p.chunk, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)tn};
+        cuuint32_t est[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+        CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, m.bufs[ti.buf], gdim, gstr, box, est,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            delete pl;
+            hbp_set_error("cuTensorMapEncodeTiled(A) failed (%d) for %s box=(%d,%d,%d,%d) stride=%d", (int)r,
+                          op.name.c_str(), p.chunk, bw, bh, tn, s);
+            return HBP_ERR_CUDA;
+        }
+    }
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)op.cin, (cuuint64_t)op.k * op.k * op.cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)op.cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)p.chunk, (cuuint32_t)n_tile};
+        cuuint32_t est[2] = {1, 1};
+        CUresult r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, m.d_weights + op.w_off, gdim, gstr, box, est,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            delete pl;
+            hbp_set_error("cuTensorMapEncodeTiled(B) failed (%d) for %s", (int)r, op.name.c_str());
+            return HBP_ERR_CUDA;
+        }
+    }
+    if (!(ctx->attr_flags & ATTR_UMMA)) {
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        ctx->attr_flags |= ATTR_UMMA;
+    }
+    *out = pl;
+    return HBP_OK;
+}
+
+int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, cudaStream_t st) {
+    (void)m; (void)op_index;
+    ConvParams p = pl->prm;
+    p.P = P;
+    const int tiles_n = (P + p.tn - 1) / p.tn;
+    dim3 grid((unsigned)(tiles_n * p.tiles_h * p.tiles_w), (unsigned)pl->n_splits);
+    conv_umma_kernel<<<grid, kThreads, pl->smem_bytes, st>>>(pl->tmA, pl->tmB, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return hbp_cuda_fail(e, "conv_umma_kernel", __FILE__, __LINE__);
+    return HBP_OK;
+}

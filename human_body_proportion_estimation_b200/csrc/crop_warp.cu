@@ -1,0 +1,202 @@
+// K4: per-person crop = batched affine warp, cv2.warpAffine-exact bilinear,
+// /255, NCHW fp16 (or fp32) HRNet input.
+//
+// Reference: models/conv.py:59-80 (tf.image.crop_and_resize of the /255 frame,
+// NHWC->NCHW) and human_body_length_est/modules/pose_estimator.py:29-45.  The
+// parity gate is cv2.warpAffine(INTER_LINEAR | WARP_INVERSE_MAP, BORDER_CONSTANT 0)
+// (BASELINE.json north_star); its arithmetic (OpenCV imgwarp.cpp, restated in
+// oracle/imgproc.py:warp_affine_cv2) is:
+//     adelta[x] = rint(M00*x*1024)          bdelta[x] = rint(M10*x*1024)
+//     X0[y] = rint((M01*y + M02)*1024) + 16  Y0[y] = rint((M11*y + M12)*1024) + 16
+//     X = (X0[y] + adelta[x]) >> 5, Y likewise       (1/32 px)
+//     sx = X >> 5, fx = X & 31 ; four taps, zero outside the frame;
+//     weights (1-fy/32)(1-fx/32)... in float32.
+// All intermediates of the blend are multiples of 2^-10 below 2^8, so float32
+// evaluates them exactly in any association.
+//
+// Work decomposition: one CTA per (person, band of kBandRows output rows).
+// The band's source bounding box is computed from the exact integer
+// coordinates of its four corners (the map is monotone in x and in y), the
+// u8 source rows of that box are staged in shared memory with 16-byte
+// coalesced loads, and every thread then produces 8 consecutive output pixels
+// per channel plane = one 16-byte fp16 store per plane.  Boxes whose band does
+// not fit the shared-memory budget (extreme zoom-out / rotation) sample global
+// memory directly through the read-only path.
+// HBM-bound: source-box bytes + 3*out_h*out_w*2 bytes per person.
+#include "hbp_internal.cuh"
+
+namespace {
+
+constexpr int kBandRows = 8;
+constexpr int kThreads = 256;
+constexpr int kSmemBudget = 64 * 1024;
+
+struct Affine {
+    double m00, m01, m02, m10, m11, m12;
+};
+
+__device__ __forceinline__ void src_coord(const Affine& A, int x, int y, int& X, int& Y) {
+    // separate roundings exactly as OpenCV (no FMA contraction)
+    const int ad = __double2int_rn(__dmul_rn(__dmul_rn(A.m00, (double)x), 1024.0));
+    const int bd = __double2int_rn(__dmul_rn(__dmul_rn(A.m10, (double)x), 1024.0));
+    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(A.m01, (double)y), A.m02), 1024.0)) + 16;
+    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(A.m11, (double)y), A.m12), 1024.0)) + 16;
+    X = (X0 + ad) >> 5;
+    Y = (Y0 + bd) >> 5;
+}
+
+template <typename OutT>
+__device__ __forceinline__ OutT to_out(float v);
+template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads)
+crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
+                 const double* __restrict__ Ms, const int* __restrict__ frame_idx, int P,
+                 int out_h, int out_w, int swap_rb, OutT* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_box[4];        // sx_min, sy_min, cols, rows (clamped to the frame)
+    __shared__ int s_use_smem;
+
+    const int p = blockIdx.y;
+    const int row0 = blockIdx.x * kBandRows;
+    const int rows = min(kBandRows, out_h - row0);
+    Affine A;
+    {
+        const double* m = Ms + (size_t)p * 6;
+        A.m00 = m[0]; A.m01 = m[1]; A.m02 = m[2]; A.m10 = m[3]; A.m11 = m[4]; A.m12 = m[5];
+    }
+    int f = frame_idx[p];
+    f = f < 0 ? 0 : (f >= n_frames ? n_frames - 1 : f);
+    const uint8_t* __restrict__ src = frames + (size_t)f * H * W * 3;
+
+    if (threadIdx.x == 0) {
+        int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+        const int cx[2] = {0, out_w - 1}, cy[2] = {row0, row0 + rows - 1};
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                int X, Y;
+                src_coord(A, cx[a], cy[b], X, Y);
+                xmin = min(xmin, X >> 5); xmax = max(xmax, X >> 5);
+                ymin = min(ymin, Y >> 5); ymax = max(ymax, Y >> 5);
+            }
+        xmax += 1; ymax += 1;                       // right / bottom taps
+        xmin = max(xmin, 0); ymin = max(ymin, 0);
+        xmax = min(xmax, W - 1); ymax = min(ymax, H - 1);
+        const int cols = xmax - xmin + 1, nrows = ymax - ymin + 1;
+        s_box[0] = xmin; s_box[1] = ymin; s_box[2] = cols; s_box[3] = nrows;
+        long long need = (cols > 0 && nrows > 0) ? (long long)nrows * (((long long)cols * 3 + 15 + 15) / 16 * 16) : 0;
+        s_use_smem = (cols > 0 && nrows > 0 && need <= kSmemBudget) ? 1 : 0;
+    }
+    __syncthreads();
+    const int bx0 = s_box[0], by0 = s_box[1], bcols = s_box[2], brows = s_box[3];
+    const bool staged = s_use_smem != 0;
+    const int pitch = ((bcols * 3 + 15 + 15) / 16) * 16;   // bytes per staged row
+
+    if (staged) {
+        // Stage rows [by0, by0+brows) x byte range of columns [bx0, bx0+bcols).
+        // Row r lives at smem[r*pitch + (addr & 15) ...]: the copy is done in
+        // 16-byte units aligned in GLOBAL memory, so every row keeps its own
+        // sub-16 phase `ph`; taps index with that phase.
+        const int chunks_per_row = pitch / 16;
+        const uint8_t* frame_end = frames + (size_t)n_frames * H * W * 3;
+        for (int t = threadIdx.x; t < brows * chunks_per_row; t += kThreads) {
+            const int r = t / chunks_per_row, c = t - r * chunks_per_row;
+            const uint8_t* g0 = src + ((size_t)(by0 + r) * W + bx0) * 3;
+            const uint8_t* ga = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(g0) & ~uintptr_t(15)) + 16 * c;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (ga >= frames && ga + 16 <= frame_end) {
+                v = __ldg(reinterpret_cast<const uint4*>(ga));
+            } else {                                    // first/last bytes of the allocation
+                uint8_t* vb = reinterpret_cast<uint8_t*>(&v);
+                for (int k = 0; k < 16; ++k)
+                    if (ga + k >= frames && ga + k < frame_end) vb[k] = __ldg(ga + k);
+            }
+            *reinterpret_cast<uint4*>(smem + (size_t)r * pitch + 16 * c) = v;
+        }
+        __syncthreads();
+    }
+
+    const int groups = (out_w + 7) / 8;                 // 8 output pixels per thread-iteration
+    const size_t plane = (size_t)out_h * out_w;
+    OutT* __restrict__ obase = out + (size_t)p * 3 * plane;
+    for (int t = threadIdx.x; t < rows * groups; t += kThreads) {
+        const int ry = t / groups, gx = t - ry * groups;
+        const int y = row0 + ry, xbeg = gx * 8;
+        OutT res[3][8];
+        // per-row constants
+        const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(A.m01, (double)y), A.m02), 1024.0)) + 16;
+        const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(A.m11, (double)y), A.m12), 1024.0)) + 16;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int x = xbeg + k;
+            const int ad = __double2int_rn(__dmul_rn(__dmul_rn(A.m00, (double)x), 1024.0));
+            const int bd = __double2int_rn(__dmul_rn(__dmul_rn(A.m10, (double)x), 1024.0));
+            const int X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
+            const int sx = X >> 5, sy = Y >> 5;
+            const float fx = (float)(X & 31) * 0.03125f, fy = (float)(Y & 31) * 0.03125f;
+            const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx;
+            const float w10 = fy * (1.f - fx), w11 = fy * fx;
+            const bool in_x0 = sx >= 0 && sx < W, in_x1 = sx + 1 >= 0 && sx + 1 < W;
+            const bool in_y0 = sy >= 0 && sy < H, in_y1 = sy + 1 >= 0 && sy + 1 < H;
+            float acc[3] = {0.f, 0.f, 0.f};
+            auto tap = [&](int yy, int xx, bool ok, float wgt) {
+                if (!ok) return;
+                const uint8_t* q;
+                if (staged) {
+                    const uint8_t* g0 = src + ((size_t)yy * W + bx0) * 3;
+                    const int ph = (int)(reinterpret_cast<uintptr_t>(g0) & 15);
+                    q = smem + (size_t)(yy - by0) * pitch + ph + (xx - bx0) * 3;
+                    acc[0] += (float)q[0] * wgt; acc[1] += (float)q[1] * wgt; acc[2] += (float)q[2] * wgt;
+                } else {
+                    q = src + ((size_t)yy * W + xx) * 3;
+                    acc[0] += (float)__ldg(q) * wgt; acc[1] += (float)__ldg(q + 1) * wgt; acc[2] += (float)__ldg(q + 2) * wgt;
+                }
+            };
+            tap(sy, sx, in_y0 && in_x0, w00);
+            tap(sy, sx + 1, in_y0 && in_x1, w01);
+            tap(sy + 1, sx, in_y1 && in_x0, w10);
+            tap(sy + 1, sx + 1, in_y1 && in_x1, w11);
+            res[0][k] = to_out<OutT>(__fdiv_rn(swap_rb ? acc[2] : acc[0], 255.0f));
+            res[1][k] = to_out<OutT>(__fdiv_rn(acc[1], 255.0f));
+            res[2][k] = to_out<OutT>(__fdiv_rn(swap_rb ? acc[0] : acc[2], 255.0f));
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            OutT* o = obase + c * plane + (size_t)y * out_w + xbeg;
+            if (xbeg + 8 <= out_w && (reinterpret_cast<uintptr_t>(o) & 15) == 0 && sizeof(OutT) == 2) {
+                *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(res[c]);
+            } else if (xbeg + 8 <= out_w && (reinterpret_cast<uintptr_t>(o) & 15) == 0 && sizeof(OutT) == 4) {
+                reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(res[c])[0];
+                reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(res[c])[1];
+            } else {
+                for (int k = 0; k < 8 && xbeg + k < out_w; ++k) o[k] = res[c][k];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int k_crop_warp(hbp_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w, const double* M,
+                const int* frame_idx, int P, int out_h, int out_w, int swap_rb, void* out,
+                int out_dtype) {
+    if (P <= 0) return HBP_OK;
+    if (!(ctx->attr_flags & ATTR_CROP)) {
+        HBP_CUDA(cudaFuncSetAttribute(crop_warp_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        HBP_CUDA(cudaFuncSetAttribute(crop_warp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        ctx->attr_flags |= ATTR_CROP;
+    }
+    dim3 grid((out_h + kBandRows - 1) / kBandRows, P);
+    if (out_dtype == HBP_F16)
+        crop_warp_kernel<__half><<<grid, kThreads, kSmemBudget, ctx->stream>>>(
+            frames, n_frames, h, w, M, frame_idx, P, out_h, out_w, swap_rb, (__half*)out);
+    else
+        crop_warp_kernel<float><<<grid, kThreads, kSmemBudget, ctx->stream>>>(
+            frames, n_frames, h, w, M, frame_idx, P, out_h, out_w, swap_rb, (float*)out);
+    HBP_LAUNCH_CHECK(ctx);
+    return HBP_OK;
+}

@@ -1,0 +1,458 @@
+// K2 / K3 / K3b: detector-head post-processing.
+//
+// Reference (relative to the reference's human_body_length_est/ unless noted):
+//   raw-head decode ....... obj_det_yolov5_onnx.py:123-169
+//   official NMS .......... modules/onnx_utils.py:125-222 -> torchvision.ops.nms (:205)
+//   legacy NMS ............ modules/onnx_utils.py:8-95
+//   scale/clip coords ..... modules/onnx_utils.py:238-266
+//   EfficientDet filter ... models/conv.py:22-57 (reference root)
+//
+// NMS pipeline, all on the device, no host round trip:
+//   1. filter    one warp per 32 rows: lanes test obj > conf on their own row
+//                (strided 4-byte reads), then the warp walks the flagged rows
+//                together: coalesced class scores, cls*obj, first-max class via
+//                shuffles, conf > thr, class filter, append to the candidate list.
+//   2. rank      stable order = (conf desc, source row asc); every candidate
+//                counts the candidates that precede it (all pairs, tiled through
+//                shared memory) and scatters itself to its rank.
+//   3. mask      bit (i,j), j>i, set iff IoU(i,j) > thr on the class-offset
+//                boxes; one warp per (row, 32-column word) builds the word with
+//                a ballot.  IoU in torchvision's operation order with explicit
+//                round-to-nearest intrinsics (no FMA contraction):
+//                inter/(area_i + area_j - inter), compared as double.
+//   4. sweep     one CTA per image walks the words in order; warp 0 resolves
+//                the 32 boxes of a word against the diagonal block with
+//                shuffles, then all threads OR the kept rows into the removed
+//                set.  Stops after max_det keeps.
+//   5. gather    writes [x1,y1,x2,y2,conf,cls] of the kept boxes (un-offset).
+// The legacy variant reuses 2-5 with key (class asc, obj desc, row asc), the
+// +1-pixel IoU, "suppress unless iou < thr" and same-class-only suppression.
+#include "hbp_internal.cuh"
+#include <algorithm>
+
+namespace {
+
+__constant__ float kAnchors[3][6] = {{116, 90, 156, 198, 373, 326},
+                                     {30, 61, 62, 45, 59, 119},
+                                     {10, 13, 16, 30, 33, 23}};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
+
+// ---- raw head decode ---------------------------------------------------------
+// in: (B,3,S,S,E) ; out rows at row_off + ((a*S + gy)*S + gx) of an image with
+// total_rows rows.  One thread per element, coalesced on E.
+__global__ void __launch_bounds__(256)
+yolo_decode_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int S, int E,
+                   int level, float stride_w, float stride_h, int row_off, int total_rows) {
+    const size_t per_img = (size_t)3 * S * S * E;
+    const size_t total = per_img * B;
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += step) {
+        const int b = (int)(t / per_img);
+        const size_t r = t % per_img;
+        const int e = (int)(r % E);
+        const size_t cell = r / E;              // (a*S + i)*S + j
+        const int j = (int)(cell % S), i = (int)((cell / S) % S), a = (int)(cell / ((size_t)S * S));
+        const float s = sigmoidf_(in[t]);
+        float v = s;
+        // the reference builds grid_x/grid_y with meshgrid(arange(shape[2]), arange(shape[3]))
+        // and adds them to a (...,S,S) tensor: grid_x varies along the LAST axis (j).
+        if (e == 0) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(s, 2.f), 0.5f), (float)j), stride_w);
+        else if (e == 1) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(s, 2.f), 0.5f), (float)i), stride_h);
+        else if (e == 2 || e == 3) {
+            const float q = __fmul_rn(s, 2.f);
+            v = __fmul_rn(__fmul_rn(q, q), kAnchors[level][2 * a + (e - 2)]);
+        }
+        out[((size_t)b * total_rows + row_off + cell) * E + e] = v;
+    }
+}
+
+// ---- candidates ---------------------------------------------------------------
+struct Cand {           // 32 bytes
+    float x1, y1, x2, y2;
+    float conf;         // official: obj*cls ; legacy: obj
+    float cls;
+    float aux;          // legacy: class confidence
+    int src;            // source row (tie-break)
+};
+
+__global__ void __launch_bounds__(256)
+yolo_filter_kernel(const float* __restrict__ pred, int N, int nc, float conf_thres, int legacy,
+                   const int* __restrict__ classes, int n_classes, Cand* __restrict__ cand,
+                   int* __restrict__ cand_count, int cap) {
+    const int b = blockIdx.y;
+    const int E = 5 + nc;
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int row0 = warp_global * 32;
+    if (row0 >= N) return;
+    const float* __restrict__ base = pred + (size_t)b * N * E;
+    const int my_row = row0 + lane;
+    float obj = 0.f;
+    bool flag = false;
+    if (my_row < N) {
+        obj = __ldg(base + (size_t)my_row * E + 4);
+        flag = legacy ? (obj >= conf_thres) : (obj > conf_thres);
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, flag);
+    while (todo) {
+        const int l = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int row = row0 + l;
+        const float* __restrict__ r = base + (size_t)row * E;
+        const float o = __shfl_sync(0xffffffffu, obj, l);
+        // first-max over classes of (cls*obj) [official] or cls [legacy]
+        float best = -INFINITY;
+        int best_j = 0x7fffffff;
+        bool any = false;
+        for (int j = lane; j < nc; j += 32) {
+            float c = __ldg(r + 5 + j);
+            if (!legacy) c = __fmul_rn(c, o);
+            // torch.max: NaN propagates as the max; first index on ties
+            if (!any) { best = c; best_j = j; any = true; }
+            else if (c > best || (c != c && best == best)) { best = c; best_j = j; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, best_j, off);
+            const bool on = ov != ov, bn = best != best;
+            bool take;
+            if (on || bn) take = on && (!bn || oj < best_j);
+            else take = ov > best || (ov == best && oj < best_j);
+            if (oj == 0x7fffffff) take = false;
+            if (best_j == 0x7fffffff && oj != 0x7fffffff) take = true;
+            if (take) { best = ov; best_j = oj; }
+        }
+        if (lane == 0) {
+            bool ok = legacy ? true : (best > conf_thres);
+            if (ok && n_classes > 0) {
+                ok = false;
+                for (int k = 0; k < n_classes; ++k) ok |= ((float)best_j == (float)classes[k]);
+            }
+            if (ok) {
+                const int slot = atomicAdd(cand_count + b, 1);
+                if (slot < cap) {
+                    const float cx = __ldg(r), cy = __ldg(r + 1), w = __ldg(r + 2), h = __ldg(r + 3);
+                    const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+                    Cand c;
+                    c.x1 = __fsub_rn(cx, hw); c.y1 = __fsub_rn(cy, hh);
+                    c.x2 = __fadd_rn(cx, hw); c.y2 = __fadd_rn(cy, hh);
+                    c.conf = legacy ? o : best;
+                    c.cls = (float)best_j;
+                    c.aux = best;
+                    c.src = row;
+                    cand[(size_t)b * cap + slot] = c;
+                }
+            }
+        }
+    }
+}
+
+// does candidate a come before candidate b in the output order?
+__device__ __forceinline__ bool precedes(float ac, float acls, int as, float bc, float bcls, int bs, int legacy) {
+    if (legacy && acls != bcls) return acls < bcls;
+    if (ac != bc) return ac > bc;
+    return as < bs;
+}
+
+struct SortedBox {      // 32 bytes
+    float x1, y1, x2, y2;   // boxes as suppressed on (class-offset for the official path)
+    float conf, cls, aux;
+    int cand;               // index into the candidate list
+};
+
+__global__ void __launch_bounds__(256)
+rank_scatter_kernel(const Cand* __restrict__ cand, const int* __restrict__ cand_count, int cap,
+                    int legacy, int max_nms, float max_wh, SortedBox* __restrict__ sorted,
+                    int* __restrict__ n_sorted) {
+    __shared__ float s_conf[256], s_cls[256];
+    __shared__ int s_src[256];
+    const int b = blockIdx.y;
+    const int n = min(cand_count[b], cap);
+    const Cand* __restrict__ c = cand + (size_t)b * cap;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x * blockDim.x >= n) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) n_sorted[b] = min(n, max_nms);
+    Cand me{};
+    if (i < n) me = c[i];
+    int rank = 0;
+    for (int t0 = 0; t0 < n; t0 += 256) {
+        const int j = t0 + threadIdx.x;
+        if (j < n) { s_conf[threadIdx.x] = c[j].conf; s_cls[threadIdx.x] = c[j].cls; s_src[threadIdx.x] = c[j].src; }
+        __syncthreads();
+        const int m = min(256, n - t0);
+        if (i < n)
+            for (int k = 0; k < m; ++k)
+                rank += precedes(s_conf[k], s_cls[k], s_src[k], me.conf, me.cls, me.src, legacy) ? 1 : 0;
+        __syncthreads();
+    }
+    if (i < n && rank < max_nms) {
+        SortedBox s;
+        // onnx_utils.py:202-204: boxes + cls * max_wh (float32 mul, float32 add)
+        const float off = legacy ? 0.f : __fmul_rn(me.cls, max_wh);
+        s.x1 = __fadd_rn(me.x1, off); s.y1 = __fadd_rn(me.y1, off);
+        s.x2 = __fadd_rn(me.x2, off); s.y2 = __fadd_rn(me.y2, off);
+        s.conf = me.conf; s.cls = me.cls; s.aux = me.aux; s.cand = i;
+        sorted[(size_t)b * cap + rank] = s;
+    }
+}
+
+__device__ __forceinline__ bool suppresses(const SortedBox& a, const SortedBox& b, double thr, int legacy) {
+    if (!legacy) {
+        // torchvision nms_kernel_impl<float>
+        const float ia = __fmul_rn(__fsub_rn(a.x2, a.x1), __fsub_rn(a.y2, a.y1));
+        const float ja = __fmul_rn(__fsub_rn(b.x2, b.x1), __fsub_rn(b.y2, b.y1));
+        const float w = fmaxf(0.f, __fsub_rn(fminf(a.x2, b.x2), fmaxf(a.x1, b.x1)));
+        const float h = fmaxf(0.f, __fsub_rn(fminf(a.y2, b.y2), fmaxf(a.y1, b.y1)));
+        const float inter = __fmul_rn(w, h);
+        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ia, ja), inter));
+        return (double)ovr > thr;
+    }
+    if (a.cls != b.cls) return false;
+    // onnx_utils.py:23-34: +1 pixel convention, +1e-16; keep while iou < thr
+    const float ix1 = fmaxf(a.x1, b.x1), iy1 = fmaxf(a.y1, b.y1);
+    const float ix2 = fminf(a.x2, b.x2), iy2 = fminf(a.y2, b.y2);
+    const float inter = __fmul_rn(fmaxf(__fadd_rn(__fsub_rn(ix2, ix1), 1.f), 0.f),
+                                  fmaxf(__fadd_rn(__fsub_rn(iy2, iy1), 1.f), 0.f));
+    const float aa = __fmul_rn(__fadd_rn(__fsub_rn(a.x2, a.x1), 1.f), __fadd_rn(__fsub_rn(a.y2, a.y1), 1.f));
+    const float ab = __fmul_rn(__fadd_rn(__fsub_rn(b.x2, b.x1), 1.f), __fadd_rn(__fsub_rn(b.y2, b.y1), 1.f));
+    const float iou = __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(aa, ab), inter), 1e-16f));
+    return !(iou < (float)thr);
+}
+
+// mask[(i*words + w)] bit l  <=>  box i suppresses box 32*w+l  (only j > i)
+__global__ void __launch_bounds__(256)
+nms_mask_kernel(const SortedBox* __restrict__ sorted, const int* __restrict__ n_sorted, int cap,
+                int words_cap, size_t mask_img_stride, double thr, int legacy, uint32_t* __restrict__ mask) {
+    const int b = blockIdx.z;
+    const int n = n_sorted[b];
+    const int words = (n + 31) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x;                       // column word
+    if (w >= words) return;
+    const SortedBox* __restrict__ s = sorted + (size_t)b * cap;
+    const int j = w * 32 + lane;
+    SortedBox bj{};
+    if (j < n) bj = s[j];
+    uint32_t* __restrict__ m = mask + (size_t)b * mask_img_stride;
+    for (int i = blockIdx.y * 8 + warp; i < n; i += gridDim.y * 8) {
+        if (w * 32 + 31 <= i) continue;             // whole word at or before the diagonal
+        const SortedBox bi = s[i];
+        const bool bit = (j < n) && (j > i) && suppresses(bi, bj, thr, legacy);
+        const uint32_t word = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) m[(size_t)i * words_cap + w] = word;
+    }
+}
+
+constexpr int kSweepThreads = 256;
+constexpr int kMaxWords = 1024;     // 32768 boxes
+
+__global__ void __launch_bounds__(kSweepThreads)
+nms_sweep_kernel(const uint32_t* __restrict__ mask, const int* __restrict__ n_sorted,
+                 int words_cap, size_t mask_img_stride, int max_keep, int* __restrict__ keep,
+                 int* __restrict__ keep_count) {
+    __shared__ uint32_t s_removed[kMaxWords];
+    __shared__ uint32_t s_keepbits;
+    __shared__ int s_kept;
+    const int b = blockIdx.x;
+    const int n = n_sorted[b];
+    const int words = (n + 31) >> 5;
+    const uint32_t* __restrict__ m = mask + (size_t)b * mask_img_stride;
+    for (int w = threadIdx.x; w < words; w += kSweepThreads) s_removed[w] = 0;
+    if (threadIdx.x == 0) s_kept = 0;
+    __syncthreads();
+    for (int w = 0; w < words; ++w) {
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            const int i = w * 32 + lane;
+            // diagonal word of my row (bits j>i inside this word); rows >= n have none
+            uint32_t diag = (i < n) ? m[(size_t)i * words_cap + w] : 0u;
+            uint32_t removed = s_removed[w];
+            if (n - w * 32 < 32) removed |= ~0u << (n - w * 32);     // padding bits
+            uint32_t keepbits = 0;
+            int kept = s_kept;
+            for (int l = 0; l < 32; ++l) {
+                const uint32_t dl = __shfl_sync(0xffffffffu, diag, l);
+                if (!((removed >> l) & 1u) && kept < max_keep) {
+                    keepbits |= 1u << l;
+                    removed |= dl;
+                    ++kept;
+                } else {
+                    removed |= 1u << l;     // not kept (suppressed or over the cap): never ORs its row
+                }
+            }
+            if (lane == 0) {
+                s_keepbits = keepbits;
+                int kk = s_kept;
+                for (uint32_t kb = keepbits; kb; kb &= kb - 1) keep[(size_t)b * max_keep + kk++] = w * 32 + __ffs(kb) - 1;
+                s_kept = kept;
+            }
+        }
+        __syncthreads();
+        const uint32_t kb = s_keepbits;
+        const bool done = s_kept >= max_keep;
+        if (kb && !done) {
+            for (int ww = w + 1 + threadIdx.x; ww < words; ww += kSweepThreads) {
+                uint32_t acc = 0;
+                for (uint32_t t = kb; t; t &= t - 1) acc |= m[(size_t)(w * 32 + __ffs(t) - 1) * words_cap + ww];
+                s_removed[ww] |= acc;
+            }
+        }
+        __syncthreads();
+        if (done) break;
+    }
+    if (threadIdx.x == 0) keep_count[b] = s_kept;
+}
+
+__global__ void nms_gather_kernel(const SortedBox* __restrict__ sorted, const Cand* __restrict__ cand,
+                                  int cap, const int* __restrict__ keep, const int* __restrict__ keep_count,
+                                  const int* __restrict__ cand_count, int max_keep, int legacy,
+                                  float* __restrict__ out, int* __restrict__ out_count) {
+    const int b = blockIdx.x;
+    const int n = keep_count[b];
+    const int width = legacy ? 7 : 6;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const SortedBox s = sorted[(size_t)b * cap + keep[(size_t)b * max_keep + k]];
+        const Cand c = cand[(size_t)b * cap + s.cand];
+        float* o = out + ((size_t)b * max_keep + k) * width;
+        o[0] = c.x1; o[1] = c.y1; o[2] = c.x2; o[3] = c.y2;
+        if (legacy) { o[4] = c.conf; o[5] = c.aux; o[6] = c.cls; }
+        else { o[4] = c.conf; o[5] = c.cls; }
+    }
+    if (threadIdx.x == 0) out_count[b] = (legacy && cand_count[b] == 0) ? -1 : n;
+}
+
+__global__ void scale_coords_kernel(float* __restrict__ boxes, int n, float pad_x, float pad_y, float gain,
+                                    float w0, float h0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float* b = boxes + 4 * (size_t)i;
+    // onnx_utils.py:262-265 then clip_coords :238-249
+    const float x1 = __fdiv_rn(__fsub_rn(b[0], pad_x), gain), y1 = __fdiv_rn(__fsub_rn(b[1], pad_y), gain);
+    const float x2 = __fdiv_rn(__fsub_rn(b[2], pad_x), gain), y2 = __fdiv_rn(__fsub_rn(b[3], pad_y), gain);
+    b[0] = fminf(fmaxf(x1, 0.f), w0); b[1] = fminf(fmaxf(y1, 0.f), h0);
+    b[2] = fminf(fmaxf(x2, 0.f), w0); b[3] = fminf(fmaxf(y2, 0.f), h0);
+}
+
+// models/conv.py:22-57: one warp per frame, ordered compaction with ballots.
+__global__ void edet_filter_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                                   const float* __restrict__ classes, int K, float person_class, float thr,
+                                   float xe, float ye, float hf, float wf, int max_persons,
+                                   float* __restrict__ out_boxes, int* __restrict__ out_count) {
+    const int f = blockIdx.x, lane = threadIdx.x;
+    int kept = 0;
+    for (int k0 = 0; k0 < K && kept < max_persons; k0 += 32) {
+        const int k = k0 + lane;
+        bool ok = false;
+        if (k < K) ok = (classes[(size_t)f * K + k] == person_class) && (scores[(size_t)f * K + k] >= thr);
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        const int pos = kept + __popc(bal & ((1u << lane) - 1u));
+        if (ok && pos < max_persons) {
+            const float* b = boxes + ((size_t)f * K + k) * 4;
+            const float y1 = fminf(fmaxf(__fsub_rn(b[0], ye), 0.f), hf), x1 = fminf(fmaxf(__fsub_rn(b[1], xe), 0.f), wf);
+            const float y2 = fminf(fmaxf(__fadd_rn(b[2], ye), 0.f), hf), x2 = fminf(fmaxf(__fadd_rn(b[3], xe), 0.f), wf);
+            float* o = out_boxes + ((size_t)f * max_persons + pos) * 4;
+            o[0] = __fdiv_rn(y1, hf); o[1] = __fdiv_rn(x1, wf); o[2] = __fdiv_rn(y2, hf); o[3] = __fdiv_rn(x2, wf);
+        }
+        kept += __popc(bal);
+    }
+    if (lane == 0) out_count[f] = min(kept, max_persons);
+}
+
+int run_nms(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, double thr,
+            const int* classes, int n_classes, int max_keep, int legacy, float* out_det, int* out_count) {
+    const int cap = N;                                   // every row can be a candidate
+    const int max_nms = legacy ? N : 30000;              // onnx_utils.py:143
+    if (N > kMaxWords * 32) { hbp_set_error("NMS supports at most %d rows per image", kMaxWords * 32); return HBP_ERR_INVALID; }
+    Cand* cand = (Cand*)hbp_scratch(ctx, SC_NMS_CAND, (size_t)B * cap * sizeof(Cand));
+    SortedBox* sorted = (SortedBox*)hbp_scratch(ctx, SC_NMS_SORTED, (size_t)B * cap * sizeof(SortedBox));
+    // misc: cand_count[B] | n_sorted[B] | keep_count[B] | keep[B*max_keep]
+    int* misc = (int*)hbp_scratch(ctx, SC_NMS_MISC, ((size_t)3 * B + (size_t)B * max_keep) * sizeof(int));
+    if (!cand || !sorted || !misc) return HBP_ERR_NOMEM;
+    int* cand_count = misc, *n_sorted = misc + B, *keep_count = misc + 2 * B, *keep = misc + 3 * B;
+    HBP_CUDA(cudaMemsetAsync(misc, 0, (size_t)3 * B * sizeof(int), ctx->stream));
+    {
+        const int warps = (N + 31) / 32;
+        dim3 grid((warps + 7) / 8, B);
+        yolo_filter_kernel<<<grid, 256, 0, ctx->stream>>>(pred, N, nc, conf, legacy, classes, n_classes, cand, cand_count, cap);
+        HBP_LAUNCH_CHECK(ctx);
+    }
+    // The candidate count decides the mask size; read it back (4*B bytes) so the
+    // mask scratch is sized for the actual n instead of N^2/8 bytes.
+    int* h_counts = (int*)hbp_pinned(ctx, (size_t)B * sizeof(int));
+    if (!h_counts) return HBP_ERR_NOMEM;
+    HBP_CUDA(cudaMemcpyAsync(h_counts, cand_count, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    HBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    int n_max = 0;
+    for (int b = 0; b < B; ++b) n_max = max(n_max, min(h_counts[b], cap));
+    n_max = min(n_max, max_nms);
+    if (n_max > 0) {
+        dim3 g1((n_max + 255) / 256, B);
+        rank_scatter_kernel<<<g1, 256, 0, ctx->stream>>>(cand, cand_count, cap, legacy, max_nms, 4096.f, sorted, n_sorted);
+        HBP_LAUNCH_CHECK(ctx);
+        const int words = (n_max + 31) / 32;
+        const size_t mask_img_stride = (size_t)n_max * words;
+        uint32_t* mask = (uint32_t*)hbp_scratch(ctx, SC_NMS_MASK, (size_t)B * mask_img_stride * sizeof(uint32_t));
+        if (!mask) return HBP_ERR_NOMEM;
+        dim3 g2(words, min((n_max + 7) / 8, 1024), B);
+        nms_mask_kernel<<<g2, 256, 0, ctx->stream>>>(sorted, n_sorted, cap, words, mask_img_stride, thr, legacy, mask);
+        HBP_LAUNCH_CHECK(ctx);
+        nms_sweep_kernel<<<B, kSweepThreads, 0, ctx->stream>>>(mask, n_sorted, words, mask_img_stride, max_keep, keep, keep_count);
+        HBP_LAUNCH_CHECK(ctx);
+    }
+    nms_gather_kernel<<<B, 128, 0, ctx->stream>>>(sorted, cand, cap, keep, keep_count, cand_count, max_keep, legacy, out_det, out_count);
+    HBP_LAUNCH_CHECK(ctx);
+    return HBP_OK;
+}
+
+}  // namespace
+
+int k_yolo_decode_raw(hbp_ctx* ctx, const float* h0, const float* h1, const float* h2, int B, int s0,
+                      int s1, int s2, int nc, int in_w, int in_h, float* out) {
+    const int E = 5 + nc;
+    const float* heads[3] = {h0, h1, h2};
+    const int S[3] = {s0, s1, s2};
+    const int total_rows = 3 * (s0 * s0 + s1 * s1 + s2 * s2);
+    int row_off = 0;
+    for (int l = 0; l < 3; ++l) {
+        // obj_det_yolov5_onnx.py:145-146: stride = int(in / feature)
+        const float sw = (float)(int)((double)in_w / S[l]), sh = (float)(int)((double)in_h / S[l]);
+        const size_t total = (size_t)B * 3 * S[l] * S[l] * E;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
+        yolo_decode_kernel<<<blocks, 256, 0, ctx->stream>>>(heads[l], out, B, S[l], E, l, sw, sh, row_off, total_rows);
+        HBP_LAUNCH_CHECK(ctx);
+        row_off += 3 * S[l] * S[l];
+    }
+    return HBP_OK;
+}
+
+int k_yolo_nms(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, double iou,
+               const int* classes, int n_classes, int max_det, float* out_det, int* out_count) {
+    return run_nms(ctx, pred, B, N, nc, conf, iou, classes, n_classes, max_det, 0, out_det, out_count);
+}
+
+int k_yolo_nms_legacy(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, float thr,
+                      int max_out, float* out_det, int* out_count) {
+    return run_nms(ctx, pred, B, N, nc, conf, (double)thr, nullptr, 0, max_out, 1, out_det, out_count);
+}
+
+int k_scale_coords(hbp_ctx* ctx, float* boxes, int n, int h1, int w1, int h0, int w0) {
+    // python: gain = max(img1)/max(img0); pad = ((w1 - w0*gain)/2, (h1 - h0*gain)/2) in double,
+    // then applied to float32 coords
+    const double gain = (double)(h1 > w1 ? h1 : w1) / (double)(h0 > w0 ? h0 : w0);
+    const double pad_x = ((double)w1 - (double)w0 * gain) / 2.0, pad_y = ((double)h1 - (double)h0 * gain) / 2.0;
+    scale_coords_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(boxes, n, (float)pad_x, (float)pad_y, (float)gain, (float)w0, (float)h0);
+    HBP_LAUNCH_CHECK(ctx);
+    return HBP_OK;
+}
+
+int k_edet_filter(hbp_ctx* ctx, const float* boxes, const float* scores, const float* classes, int F,
+                  int K, float person_class, float thr, float xe, float ye, int img_h, int img_w,
+                  int max_persons, float* out_boxes, int* out_count) {
+    HBP_CUDA(cudaMemsetAsync(out_boxes, 0, (size_t)F * max_persons * 4 * sizeof(float), ctx->stream));
+    edet_filter_kernel<<<F, 32, 0, ctx->stream>>>(boxes, scores, classes, K, person_class, thr, xe, ye,
+                                                  (float)img_h, (float)img_w, max_persons, out_boxes, out_count);
+    HBP_LAUNCH_CHECK(ctx);
+    return HBP_OK;
+}

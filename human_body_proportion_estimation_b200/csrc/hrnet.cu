@@ -1,0 +1,693 @@
+// K5: HRNet-W32 / W48 pose network (public "pose_hrnet" definition, Sun et al.
+// CVPR 2019) as a flat program of fused convolutions over NHWC fp16 tensors.
+//
+// Replaces the opaque network behind the reference's
+// human_body_length_est/modules/pose_estimator.py:47-59 (onnxruntime session)
+// and the Triton `hrnet` model of the ensemble
+// (human_body_length_est/person_det_pose_edet4_trtserver.py:22-23).  The
+// reference ships no network source; layer names follow the public HRNet
+// state_dict so that real checkpoints map one to one.
+//
+// Every op is  out = act(conv(in) + bias [+ residual])  with BatchNorm folded
+// into the weights at load time, optionally with the nearest-neighbour
+// upsample of the fuse layers folded into the store.  Two engines execute the
+// same program:
+//   engine 0  SIMT implicit-GEMM tiles (this file)  -- any shape, the checker
+//   engine 1  tcgen05/TMEM implicit GEMM fed by TMA (conv_umma.cu)
+// The four resolution branches of a stage run on four streams; the whole
+// forward is captured into one CUDA graph per (batch, buffers) key.
+#include "hrnet.cuh"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+// ===========================================================================
+// Program builder
+// ===========================================================================
+namespace {
+
+struct Builder {
+    HrnetModel& m;
+    // free buffers by size: usable by everyone / usable by one stream / waiting for the next join
+    std::multimap<size_t, int> free_all;
+    std::multimap<size_t, int> free_stream[4];
+    std::vector<std::pair<size_t, int>> pending;
+    int cur_stream = 0;
+    bool pending_join = false;
+
+    explicit Builder(HrnetModel& mm) : m(mm) {}
+
+    int new_tensor(int c, int h, int w) {
+        HTensor t;
+        t.c = c; t.h = h; t.w = w;
+        const size_t sz = (size_t)c * h * w;
+        auto take = [&](std::multimap<size_t, int>& pool) {
+            auto it = pool.find(sz);
+            if (it == pool.end()) return -1;
+            int b = it->second;
+            pool.erase(it);
+            return b;
+        };
+        int b = take(free_stream[cur_stream]);
+        if (b < 0) b = take(free_all);
+        if (b < 0) {
+            b = m.n_bufs++;
+            m.buf_elems_per_image.push_back(sz);
+        }
+        t.buf = b;
+        m.tensors.push_back(t);
+        return (int)m.tensors.size() - 1;
+    }
+    // tensor no longer needed by ops issued so far.  same_stream_only: every reader
+    // ran on cur_stream, so that stream may reuse the buffer at once.
+    void release(int tid, bool same_stream_only) {
+        const HTensor& t = m.tensors[tid];
+        const size_t sz = (size_t)t.c * t.h * t.w;
+        if (same_stream_only) free_stream[cur_stream].insert({sz, t.buf});
+        else pending.push_back({sz, t.buf});
+    }
+    void join() {          // next op carries a global join
+        pending_join = true;
+        for (auto& p : pending) free_all.insert(p);
+        pending.clear();
+        for (int s = 0; s < 4; ++s) {
+            for (auto& p : free_stream[s]) free_all.insert(p);
+            free_stream[s].clear();
+        }
+    }
+    int conv(const std::string& name, int in, int cout, int k, int stride, int relu, int res = -1,
+             int out = -1, int up = 1) {
+        const HTensor ti = m.tensors[in];
+        HOp op;
+        op.kind = OP_CONV;
+        op.name = name;
+        op.in = in;
+        op.cin = ti.c; op.cout = cout; op.k = k; op.stride = stride; op.up = up; op.relu = relu;
+        op.res = res;
+        if (out < 0) out = new_tensor(cout, ti.h / stride * up, ti.w / stride * up);
+        op.out = out;
+        op.w_off = m.n_weights;
+        op.b_off = m.n_biases;
+        m.n_weights += (size_t)k * k * cout * ti.c;
+        m.n_biases += cout;
+        op.stream = cur_stream;
+        op.join_before = pending_join ? 1 : 0;
+        pending_join = false;
+        m.ops.push_back(op);
+        return out;
+    }
+};
+
+std::string S(const char* fmt, int a = 0, int b = 0, int c = 0, int d = 0) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), fmt, a, b, c, d);
+    return buf;
+}
+
+// one HighResolutionModule: `nb` branches x 4 BasicBlocks, then the fuse layers
+void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const std::vector<int>& ch,
+                  bool multi_scale_output) {
+    HrnetModel& m = B.m;
+    const int nb = (int)x.size();
+    for (int i = 0; i < nb; ++i) {
+        B.cur_stream = i;
+        for (int blk = 0; blk < 4; ++blk) {
+            const std::string p = pre + S(".branches.%d.%d", i, blk);
+            const int t = B.conv(p + ".conv1", x[i], ch[i], 3, 1, 1);
+            const int y = B.conv(p + ".conv2", t, ch[i], 3, 1, 1, /*res=*/x[i]);
+            B.release(t, true);
+            // the module input of blk 0 may have been produced on another stream /
+            // is shared: only tensors created inside this loop are stream-local
+            B.release(x[i], blk > 0);
+            x[i] = y;
+        }
+    }
+    // fuse: y_i = relu( sum_j f_ij(x_j) ), f_ii = identity
+    B.join();
+    const int n_out = multi_scale_output ? nb : 1;
+    std::vector<int> y(n_out);
+    for (int i = 0; i < n_out; ++i) {
+        B.cur_stream = i;
+        const HTensor ti = m.tensors[x[i]];
+        y[i] = B.new_tensor(ti.c, ti.h, ti.w);
+        int res = x[i];                    // first term adds the identity branch
+        int remaining = nb - 1;
+        for (int j = 0; j < nb; ++j) {
+            if (j == i) continue;
+            --remaining;
+            const int last = remaining == 0;
+            if (j > i) {
+                B.conv(pre + S(".fuse_layers.%d.%d.0", i, j), x[j], ch[i], 1, 1, last, res, y[i], 1 << (j - i));
+            } else {
+                int cur = x[j];
+                for (int k = 0; k < i - j; ++k) {
+                    const std::string nm = pre + S(".fuse_layers.%d.%d.%d.0", i, j, k);
+                    if (k == i - j - 1) {
+                        B.conv(nm, cur, ch[i], 3, 2, last, res, y[i]);
+                        if (cur != x[j]) B.release(cur, true);
+                    } else {
+                        const int nxt = B.conv(nm, cur, ch[j], 3, 2, 1);
+                        if (cur != x[j]) B.release(cur, true);
+                        cur = nxt;
+                    }
+                }
+            }
+            res = y[i];
+        }
+    }
+    for (int j = 0; j < nb; ++j) B.release(x[j], false);
+    B.join();
+    x = y;
+}
+
+}  // namespace
+
+void hrnet_build_program(HrnetModel& m) {
+    m.tensors.clear(); m.ops.clear(); m.buf_elems_per_image.clear();
+    m.n_bufs = 0; m.n_weights = 0; m.n_biases = 0;
+    Builder B(m);
+    const int C = m.width;
+    const int H2 = m.in_h / 2, W2 = m.in_w / 2;
+    // stem
+    {
+        HOp op;
+        op.kind = OP_STEM1; op.name = "conv1";
+        op.cin = 3; op.cout = 64; op.k = 3; op.stride = 2; op.relu = 1;
+        op.out = B.new_tensor(64, H2, W2);
+        op.w_off = m.n_weights; op.b_off = m.n_biases;
+        m.n_weights += 9 * 64 * 3; m.n_biases += 64;
+        m.ops.push_back(op);
+    }
+    int x = B.conv("conv2", m.ops[0].out, 64, 3, 2, 1);
+    B.release(m.ops[0].out, true);
+    // layer1: 4 Bottlenecks (64 -> 256)
+    for (int b = 0; b < 4; ++b) {
+        const std::string p = S("layer1.%d", b);
+        int res = x;
+        if (b == 0) res = B.conv(p + ".downsample.0", x, 256, 1, 1, 0);
+        const int t1 = B.conv(p + ".conv1", x, 64, 1, 1, 1);
+        const int t2 = B.conv(p + ".conv2", t1, 64, 3, 1, 1);
+        B.release(t1, true);
+        const int y = B.conv(p + ".conv3", t2, 256, 1, 1, 1, res);
+        B.release(t2, true);
+        if (res != x) B.release(res, true);
+        B.release(x, true);
+        x = y;
+    }
+    // transition1
+    std::vector<int> xs(2);
+    xs[0] = B.conv("transition1.0.0", x, C, 3, 1, 1);
+    xs[1] = B.conv("transition1.1.0.0", x, 2 * C, 3, 2, 1);
+    B.release(x, true);
+    B.join();
+    std::vector<int> ch = {C, 2 * C};
+    stage_module(B, "stage2.0", xs, ch, true);
+    // transition2: new branch from the last branch
+    B.cur_stream = 2;
+    xs.push_back(B.conv("transition2.2.0.0", xs[1], 4 * C, 3, 2, 1));
+    ch.push_back(4 * C);
+    for (int mod = 0; mod < 4; ++mod) stage_module(B, S("stage3.%d", mod), xs, ch, true);
+    B.cur_stream = 3;
+    xs.push_back(B.conv("transition3.3.0.0", xs[2], 8 * C, 3, 2, 1));
+    ch.push_back(8 * C);
+    for (int mod = 0; mod < 3; ++mod) stage_module(B, S("stage4.%d", mod), xs, ch, mod < 2);
+    // head
+    {
+        B.cur_stream = 0;
+        HOp op;
+        op.kind = OP_HEAD; op.name = "final_layer";
+        op.in = xs[0];
+        op.cin = C; op.cout = 17; op.k = 1; op.stride = 1;
+        op.w_off = m.n_weights; op.b_off = m.n_biases;
+        m.n_weights += (size_t)17 * C; m.n_biases += 17;
+        op.join_before = 1;
+        m.ops.push_back(op);
+    }
+}
+
+// ===========================================================================
+// Engine 0 kernels
+// ===========================================================================
+namespace {
+
+// conv1: NCHW fp16 (P,3,H,W) -> NHWC fp16 (P,H/2,W/2,64), 3x3 stride 2 pad 1, +bias, ReLU
+__global__ void __launch_bounds__(128)
+stem1_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const float* __restrict__ bias,
+             __half* __restrict__ out, int P, int H, int W) {
+    __shared__ float s_w[64 * 27];      // [co][tap*3 + ci]
+    __shared__ float s_b[64];
+    for (int i = threadIdx.x; i < 64 * 27; i += blockDim.x) {
+        const int co = i / 27, r = i % 27, tap = r / 3, ci = r % 3;
+        s_w[i] = __half2float(w[((size_t)tap * 64 + co) * 3 + ci]);      // blob layout [tap][co][ci]
+    }
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_b[i] = bias[i];
+    __syncthreads();
+    const int Ho = H / 2, Wo = W / 2;
+    const size_t total = (size_t)P * Ho * Wo;
+    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= total) return;
+    const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((size_t)Wo * Ho));
+    float v[27];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const int hi = ho * 2 + dy - 1, wi = wo * 2 + dx - 1;
+            const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci)
+                v[(dy * 3 + dx) * 3 + ci] = ok ? __half2float(in[(((size_t)n * 3 + ci) * H + hi) * W + wi]) : 0.f;
+        }
+    __half* o = out + pix * 64;
+    for (int g = 0; g < 8; ++g) {
+        __align__(16) __half r[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float* ww = s_w + (g * 8 + c) * 27;
+            float acc = s_b[g * 8 + c];
+#pragma unroll
+            for (int t = 0; t < 27; ++t) acc = fmaf(v[t], ww[t], acc);
+            r[c] = __float2half_rn(fmaxf(acc, 0.f));
+        }
+        *reinterpret_cast<uint4*>(o + g * 8) = *reinterpret_cast<const uint4*>(r);
+    }
+}
+
+// final_layer: NHWC fp16 (P,Hh,Wh,C) -> NCHW (P,17,Hh,Wh) fp16|fp32, 1x1 + bias
+template <typename OutT>
+__global__ void __launch_bounds__(128)
+head_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const float* __restrict__ bias,
+            OutT* __restrict__ out, int P, int HW, int C) {
+    extern __shared__ float s_hw[];          // [17][C] then bias[17]
+    for (int i = threadIdx.x; i < 17 * C; i += blockDim.x) s_hw[i] = __half2float(w[i]);
+    for (int i = threadIdx.x; i < 17; i += blockDim.x) s_hw[17 * C + i] = bias[i];
+    __syncthreads();
+    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (size_t)P * HW) return;
+    const int n = (int)(pix / HW), hw = (int)(pix % HW);
+    float acc[17];
+#pragma unroll
+    for (int j = 0; j < 17; ++j) acc[j] = s_hw[17 * C + j];
+    const uint4* src = reinterpret_cast<const uint4*>(in + pix * C);
+    for (int c8 = 0; c8 < C / 8; ++c8) {
+        const uint4 q = __ldg(src + c8);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 t = __half22float2(h2[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+#pragma unroll
+        for (int j = 0; j < 17; ++j) {
+            const float* ww = s_hw + j * C + c8 * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[j] = fmaf(f[k], ww[k], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 17; ++j) {
+        OutT* o = out + ((size_t)n * 17 + j) * HW + hw;
+        if constexpr (sizeof(OutT) == 2) *o = __float2half_rn(acc[j]);
+        else *o = acc[j];
+    }
+}
+
+// Generic fused conv, NHWC fp16, weights [tap][cout][cin], fp32 accumulate.
+// CTA tile: 64 output pixels x 64 output channels, 256 threads, 4x4 per thread.
+constexpr int kTP = 64, kTC = 64, kTK = 32;
+
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const float* __restrict__ bias,
+                 const __half* res, __half* out, int P, int Hi, int Wi, int Cin, int Ho, int Wo,
+                 int Cout, int k, int stride, int up, int relu) {
+    __shared__ __align__(16) float As[kTK][kTP + 4];
+    __shared__ __align__(16) float Bs[kTK][kTC + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const size_t total_px = (size_t)P * Ho * Wo;
+    const size_t px0 = (size_t)blockIdx.x * kTP;
+    const int co0 = blockIdx.y * kTC;
+    const int pad = k / 2;
+    // loader mapping: 4 threads per row, 8 channels (16 B) each
+    const int lrow = tid >> 2, lci = (tid & 3) * 8;
+    const size_t lpx = px0 + lrow;
+    int ln = 0, lho = 0, lwo = 0;
+    const bool lpx_ok = lpx < total_px;
+    if (lpx_ok) { lwo = (int)(lpx % Wo); lho = (int)((lpx / Wo) % Ho); ln = (int)(lpx / ((size_t)Wo * Ho)); }
+    const int lco = co0 + lrow;
+    float acc[4][4] = {};
+    for (int tap = 0; tap < k * k; ++tap) {
+        const int dy = tap / k - pad, dx = tap % k - pad;
+        const int hi = lho * stride + dy, wi = lwo * stride + dx;
+        const bool a_ok = lpx_ok && hi >= 0 && hi < Hi && wi >= 0 && wi < Wi;
+        const __half* a_src = in + (((size_t)ln * Hi + hi) * Wi + wi) * Cin;
+        const __half* b_src = w + ((size_t)tap * Cout + lco) * Cin;
+        for (int c0 = 0; c0 < Cin; c0 += kTK) {
+            uint4 qa = make_uint4(0, 0, 0, 0), qb = make_uint4(0, 0, 0, 0);
+            const bool c_ok = c0 + lci < Cin;
+            if (a_ok && c_ok) qa = __ldg(reinterpret_cast<const uint4*>(a_src + c0 + lci));
+            if (lco < Cout && c_ok) qb = __ldg(reinterpret_cast<const uint4*>(b_src + c0 + lci));
+            const __half2* ha = reinterpret_cast<const __half2*>(&qa);
+            const __half2* hb = reinterpret_cast<const __half2*>(&qb);
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 fa = __half22float2(ha[q]), fb = __half22float2(hb[q]);
+                As[lci + 2 * q][lrow] = fa.x; As[lci + 2 * q + 1][lrow] = fa.y;
+                Bs[lci + 2 * q][lrow] = fb.x; Bs[lci + 2 * q + 1][lrow] = fb.y;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int kk = 0; kk < kTK; ++kk) {
+                const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+                const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+        }
+    }
+    // epilogue
+    const int co = co0 + tx * 4;
+    if (co >= Cout) return;
+    float bz[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bz[j] = (co + j < Cout) ? bias[co + j] : 0.f;
+    const int Hout = Ho * up, Wout = Wo * up;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const size_t px = px0 + ty * 4 + i;
+        if (px >= total_px) continue;
+        const int wo = (int)(px % Wo), ho = (int)((px / Wo) % Ho), n = (int)(px / ((size_t)Wo * Ho));
+        for (int uy = 0; uy < up; ++uy)
+            for (int ux = 0; ux < up; ++ux) {
+                const size_t o = ((((size_t)n * Hout + ho * up + uy) * Wout) + wo * up + ux) * Cout + co;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bz[j];
+                if (res) {
+                    const uint2 q = *reinterpret_cast<const uint2*>(res + o);
+                    const __half2* h = reinterpret_cast<const __half2*>(&q);
+                    const float2 r0 = __half22float2(h[0]), r1 = __half22float2(h[1]);
+                    v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                __align__(8) __half2 pk[2] = {__floats2half2_rn(v[0], v[1]), __floats2half2_rn(v[2], v[3])};
+                *reinterpret_cast<uint2*>(out + o) = *reinterpret_cast<const uint2*>(pk);
+            }
+    }
+}
+
+}  // namespace
+
+// ===========================================================================
+// Executor
+// ===========================================================================
+void hrnet_dims(hbp_ctx* ctx, int* h, int* w, int* width) {
+    *h = ctx->hrnet ? ctx->hrnet->in_h : 0;
+    *w = ctx->hrnet ? ctx->hrnet->in_w : 0;
+    *width = ctx->hrnet ? ctx->hrnet->width : 0;
+}
+
+static void free_batch_state(hbp_ctx* ctx, HrnetModel* m) {
+    cudaStreamSynchronize(ctx->stream);
+    if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+    for (UmmaPlan* p : m->umma) if (p) umma_plan_destroy(p);
+    m->umma.clear();
+    for (__half* b : m->bufs) if (b) cudaFree(b);
+    m->bufs.clear();
+    m->cap_P = 0;
+    m->graph_P = 0;
+}
+
+void hrnet_free(hbp_ctx* ctx) {
+    HrnetModel* m = ctx->hrnet;
+    if (!m) return;
+    free_batch_state(ctx, m);
+    if (m->d_weights) cudaFree(m->d_weights);
+    if (m->d_bias) cudaFree(m->d_bias);
+    for (int i = 0; i < 3; ++i) {
+        if (m->side[i]) cudaStreamDestroy(m->side[i]);
+        if (m->ev_join[i]) cudaEventDestroy(m->ev_join[i]);
+    }
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
+    delete m;
+    ctx->hrnet = nullptr;
+}
+
+int hrnet_load(hbp_ctx* ctx, int width, int in_h, int in_w, const void* w16, size_t nw,
+               const float* bias, size_t nb) {
+    hrnet_free(ctx);
+    HrnetModel* m = new HrnetModel();
+    m->width = width; m->in_h = in_h; m->in_w = in_w;
+    hrnet_build_program(*m);
+    if (nw != m->n_weights || nb != m->n_biases) {
+        hbp_set_error("HRNet-W%d expects %zu weights and %zu biases, got %zu / %zu", width, m->n_weights,
+                      m->n_biases, nw, nb);
+        delete m;
+        return HBP_ERR_INVALID;
+    }
+    ctx->hrnet = m;
+    HBP_CUDA(cudaMalloc(&m->d_weights, nw * sizeof(__half)));
+    HBP_CUDA(cudaMalloc(&m->d_bias, nb * sizeof(float)));
+    HBP_CUDA(cudaMemcpyAsync(m->d_weights, w16, nw * sizeof(__half), cudaMemcpyHostToDevice, ctx->stream));
+    HBP_CUDA(cudaMemcpyAsync(m->d_bias, bias, nb * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    for (int i = 0; i < 3; ++i) {
+        HBP_CUDA(cudaStreamCreateWithFlags(&m->side[i], cudaStreamNonBlocking));
+        HBP_CUDA(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
+    }
+    HBP_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    HBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    m->engine = 1;
+    return HBP_OK;
+}
+
+int hrnet_set_engine(hbp_ctx* ctx, int engine) {
+    if (!ctx->hrnet) { hbp_set_error("no model loaded"); return HBP_ERR_STATE; }
+    if (engine != 0 && engine != 1) { hbp_set_error("engine must be 0 (SIMT) or 1 (tcgen05)"); return HBP_ERR_INVALID; }
+    ctx->hrnet->engine = engine;
+    return HBP_OK;
+}
+
+static int ensure_batch(hbp_ctx* ctx, HrnetModel* m, int P) {
+    if (P <= m->cap_P) return HBP_OK;
+    free_batch_state(ctx, m);
+    int cap = 8;
+    while (cap < P) cap *= 2;
+    m->bufs.assign(m->n_bufs, nullptr);
+    for (int b = 0; b < m->n_bufs; ++b)
+        HBP_CUDA(cudaMalloc(&m->bufs[b], m->buf_elems_per_image[b] * (size_t)cap * sizeof(__half)));
+    m->cap_P = cap;
+    m->umma.assign(m->ops.size(), nullptr);
+    return HBP_OK;
+}
+
+static cudaStream_t stream_of(hbp_ctx* ctx, HrnetModel* m, int s) { return s == 0 ? ctx->stream : m->side[s - 1]; }
+
+// all four streams wait for each other (also used to fork at the start / join at the end)
+static int join_all(hbp_ctx* ctx, HrnetModel* m) {
+    for (int s = 1; s < 4; ++s) {
+        HBP_CUDA(cudaEventRecord(m->ev_join[s - 1], stream_of(ctx, m, s)));
+        HBP_CUDA(cudaStreamWaitEvent(ctx->stream, m->ev_join[s - 1], 0));
+    }
+    HBP_CUDA(cudaEventRecord(m->ev_fork, ctx->stream));
+    for (int s = 1; s < 4; ++s) HBP_CUDA(cudaStreamWaitEvent(stream_of(ctx, m, s), m->ev_fork, 0));
+    return HBP_OK;
+}
+
+static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, void* heatmaps, int out_dtype,
+                     uint64_t* n_launch) {
+    // fork: side streams join the origin stream (required for capture)
+    HBP_CUDA(cudaEventRecord(m->ev_fork, ctx->stream));
+    for (int s = 1; s < 4; ++s) HBP_CUDA(cudaStreamWaitEvent(stream_of(ctx, m, s), m->ev_fork, 0));
+    uint64_t launches = 0;
+    for (size_t i = 0; i < m->ops.size(); ++i) {
+        const HOp& op = m->ops[i];
+        if (op.join_before) { int s = join_all(ctx, m); if (s) return s; }
+        cudaStream_t st = stream_of(ctx, m, op.stream);
+        if (op.kind == OP_STEM1) {
+            const HTensor& to = m->tensors[op.out];
+            const size_t total = (size_t)P * to.h * to.w;
+            stem1_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+                crops, m->d_weights + op.w_off, m->d_bias + op.b_off, m->bufs[to.buf], P, m->in_h, m->in_w);
+        } else if (op.kind == OP_HEAD) {
+            const HTensor& ti = m->tensors[op.in];
+            const size_t total = (size_t)P * ti.h * ti.w;
+            const size_t sm = (size_t)(17 * ti.c + 17) * sizeof(float);
+            if (out_dtype == HBP_F16)
+                head_kernel<__half><<<(unsigned)((total + 127) / 128), 128, sm, st>>>(
+                    m->bufs[ti.buf], m->d_weights + op.w_off, m->d_bias + op.b_off, (__half*)heatmaps, P, ti.h * ti.w, ti.c);
+            else
+                head_kernel<float><<<(unsigned)((total + 127) / 128), 128, sm, st>>>(
+                    m->bufs[ti.buf], m->d_weights + op.w_off, m->d_bias + op.b_off, (float*)heatmaps, P, ti.h * ti.w, ti.c);
+        } else {
+            bool done = false;
+            if (m->engine == 1 && umma_supported(*m, op)) {
+                if (!m->umma[i]) {
+                    int s = umma_plan_create(ctx, *m, (int)i, m->cap_P, &m->umma[i]);
+                    if (s) return s;
+                }
+                int s = umma_launch(ctx, *m, (int)i, m->umma[i], P, st);
+                if (s) return s;
+                done = true;
+            }
+            if (!done) {
+                const HTensor& ti = m->tensors[op.in];
+                const int Ho = ti.h / op.stride, Wo = ti.w / op.stride;
+                const size_t total = (size_t)P * Ho * Wo;
+                dim3 grid((unsigned)((total + kTP - 1) / kTP), (op.cout + kTC - 1) / kTC);
+                conv_simt_kernel<<<grid, 256, 0, st>>>(
+                    m->bufs[ti.buf], m->d_weights + op.w_off, m->d_bias + op.b_off,
+                    op.res >= 0 ? m->bufs[m->tensors[op.res].buf] : nullptr, m->bufs[m->tensors[op.out].buf],
+                    P, ti.h, ti.w, op.cin, Ho, Wo, op.cout, op.k, op.stride, op.up, op.relu);
+            }
+        }
+        ++launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return hbp_cuda_fail(e, op.name.c_str(), __FILE__, __LINE__);
+    }
+    // final join back into the origin stream
+    for (int s = 1; s < 4; ++s) {
+        HBP_CUDA(cudaEventRecord(m->ev_join[s - 1], stream_of(ctx, m, s)));
+        HBP_CUDA(cudaStreamWaitEvent(ctx->stream, m->ev_join[s - 1], 0));
+    }
+    *n_launch = launches;
+    return HBP_OK;
+}
+
+int hrnet_forward(hbp_ctx* ctx, const __half* crops, int P, void* heatmaps, int out_dtype) {
+    HrnetModel* m = ctx->hrnet;
+    if (!m) { hbp_set_error("no model loaded"); return HBP_ERR_STATE; }
+    int s = ensure_batch(ctx, m, P);
+    if (s) return s;
+    const bool same_key = m->graph_exec && m->graph_P == P && m->graph_dtype == out_dtype &&
+                          m->graph_in == (const void*)crops && m->graph_out == heatmaps &&
+                          m->graph_engine == m->engine;
+    static const bool no_graph = getenv("HBP_NO_GRAPH") != nullptr;
+    if (same_key && !no_graph) {
+        HBP_CUDA(cudaGraphLaunch(m->graph_exec, ctx->stream));
+        ctx->launches += m->graph_nodes;
+        return HBP_OK;
+    }
+    const bool seen_before = m->graph_P == P && m->graph_dtype == out_dtype && m->graph_in == (const void*)crops &&
+                             m->graph_out == heatmaps && m->graph_engine == m->engine;
+    uint64_t n = 0;
+    if (seen_before && !no_graph) {
+        // second consecutive call with the same key: capture it (plans already exist, so no
+        // allocation or tensor-map encoding happens inside the capture)
+        if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+        cudaGraph_t g = nullptr;
+        HBP_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        s = issue_ops(ctx, m, crops, P, heatmaps, out_dtype, &n);
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        if (s) { if (g) cudaGraphDestroy(g); return s; }
+        if (e != cudaSuccess) return hbp_cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+        e = cudaGraphInstantiate(&m->graph_exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { m->graph_exec = nullptr; return hbp_cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+        m->graph_nodes = n;
+        HBP_CUDA(cudaGraphLaunch(m->graph_exec, ctx->stream));
+        ctx->launches += n;
+        return HBP_OK;
+    }
+    if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+    s = issue_ops(ctx, m, crops, P, heatmaps, out_dtype, &n);
+    if (s) return s;
+    ctx->launches += n;
+    m->graph_P = P; m->graph_dtype = out_dtype; m->graph_in = crops; m->graph_out = heatmaps;
+    m->graph_engine = m->engine;
+    return HBP_OK;
+}
+
+int hrnet_debug_tensor(hbp_ctx* ctx, int id, void* out_host, size_t max_bytes, int* n, int* h, int* w, int* c) {
+    HrnetModel* m = ctx->hrnet;
+    if (!m || m->cap_P == 0) { hbp_set_error("no forward has run"); return HBP_ERR_STATE; }
+    if (id < 0 || id >= (int)m->ops.size() || m->ops[id].out < 0) { hbp_set_error("bad op index"); return HBP_ERR_INVALID; }
+    const HTensor& t = m->tensors[m->ops[id].out];
+    const int P = m->graph_P;
+    const size_t bytes = (size_t)P * t.c * t.h * t.w * sizeof(__half);
+    if (n) *n = P; if (h) *h = t.h; if (w) *w = t.w; if (c) *c = t.c;
+    if (!out_host) return HBP_OK;
+    if (bytes > max_bytes) { hbp_set_error("buffer too small"); return HBP_ERR_OVERFLOW; }
+    HBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    HBP_CUDA(cudaMemcpy(out_host, m->bufs[t.buf], bytes, cudaMemcpyDeviceToHost));
+    return HBP_OK;
+}
+
+// One fused convolution on caller-provided device buffers (NHWC fp16), through either
+// engine: the unit-test / bring-up entry for the conv kernels.
+int hrnet_single_conv(hbp_ctx* ctx, int engine, const __half* in, int P, int H, int W, int Cin,
+                      const __half* w, const float* bias, const __half* res, int Cout, int k, int stride,
+                      int up, int relu, __half* out, int* used_engine) {
+    HrnetModel m;
+    HTensor ti; ti.c = Cin; ti.h = H; ti.w = W; ti.buf = 0;
+    HTensor to; to.c = Cout; to.h = H / stride * up; to.w = W / stride * up; to.buf = 1;
+    HTensor tr = to; tr.buf = 2;
+    m.tensors = {ti, to, tr};
+    m.bufs = {const_cast<__half*>(in), out, const_cast<__half*>(res)};
+    m.d_weights = const_cast<__half*>(w);
+    m.d_bias = const_cast<float*>(bias);
+    HOp op;
+    op.kind = OP_CONV; op.name = "single"; op.in = 0; op.out = 1; op.res = res ? 2 : -1;
+    op.cin = Cin; op.cout = Cout; op.k = k; op.stride = stride; op.up = up; op.relu = relu;
+    m.ops = {op};
+    int status = HBP_OK;
+    if (engine == 1 && umma_supported(m, op)) {
+        UmmaPlan* plan = nullptr;
+        status = umma_plan_create(ctx, m, 0, P, &plan);
+        if (status == HBP_OK) {
+            status = umma_launch(ctx, m, 0, plan, P, ctx->stream);
+            // the tensor maps are kernel parameters (copied at launch): the plan can go
+            umma_plan_destroy(plan);
+        }
+        if (used_engine) *used_engine = 1;
+    } else {
+        const int Ho = H / stride, Wo = W / stride;
+        const size_t total = (size_t)P * Ho * Wo;
+        dim3 grid((unsigned)((total + kTP - 1) / kTP), (Cout + kTC - 1) / kTC);
+        conv_simt_kernel<<<grid, 256, 0, ctx->stream>>>(in, w, bias, res, out, P, H, W, Cin, Ho, Wo, Cout, k,
+                                                        stride, up, relu);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) status = hbp_cuda_fail(e, "conv_simt_kernel", __FILE__, __LINE__);
+        if (used_engine) *used_engine = 0;
+    }
+    m.d_weights = nullptr; m.d_bias = nullptr; m.bufs.clear();
+    ctx->launches++;
+    return status;
+}
+
+// host-only description of the program (no context needed): one line per conv
+//   name cin cout k stride w_off b_off
+extern "C" int hbp_hrnet_describe(int width, int in_h, int in_w, char* buf, size_t buf_bytes,
+                                          size_t* n_weights, size_t* n_biases, size_t* needed) {
+    if ((width != 32 && width != 48) || in_h % 32 || in_w % 32 || in_h <= 0 || in_w <= 0) {
+        hbp_set_error("hbp_hrnet_describe: bad architecture");
+        return HBP_ERR_INVALID;
+    }
+    HrnetModel m;
+    m.width = width; m.in_h = in_h; m.in_w = in_w;
+    hrnet_build_program(m);
+    std::string s;
+    char line[256];
+    for (const HOp& op : m.ops) {
+        snprintf(line, sizeof(line), "%s %d %d %d %d %zu %zu\n", op.name.c_str(), op.cin, op.cout, op.k,
+                 op.stride, op.w_off, op.b_off);
+        s += line;
+    }
+    if (n_weights) *n_weights = m.n_weights;
+    if (n_biases) *n_biases = m.n_biases;
+    if (needed) *needed = s.size() + 1;
+    if (buf && buf_bytes > 0) {
+        const size_t k = std::min(buf_bytes - 1, s.size());
+        memcpy(buf, s.data(), k);
+        buf[k] = 0;
+        if (k < s.size()) return HBP_ERR_OVERFLOW;
+    }
+    return HBP_OK;
+}

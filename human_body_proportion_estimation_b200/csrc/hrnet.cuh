@@ -1,0 +1,64 @@
+// HRNet program representation shared by hrnet.cu (builder / executor / SIMT
+// kernels) and conv_umma.cu (tcgen05 implicit-GEMM engine).
+#pragma once
+#include "hbp_internal.cuh"
+#include <cuda.h>
+#include <string>
+#include <vector>
+
+// One activation tensor, NHWC fp16: (P, h, w, c); batch dimension decided at run time.
+struct HTensor {
+    int c = 0, h = 0, w = 0;
+    int buf = -1;               // index into the per-batch buffer table
+};
+
+enum HOpKind { OP_STEM1 = 0, OP_CONV = 1, OP_HEAD = 2 };
+
+// out = act( conv_k,s(in) + bias [+ residual] ), optionally replicated `up` x `up`
+// (nearest upsample fused into the store; residual is read at the upsampled position)
+struct HOp {
+    int kind = OP_CONV;
+    std::string name;           // public HRNet state_dict prefix, e.g. "stage2.0.branches.1.0.conv1"
+    int in = -1, out = -1, res = -1;   // tensor ids (res = -1: none; may equal out: in-place accumulate)
+    int cin = 0, cout = 0, k = 1, stride = 1, up = 1;
+    int relu = 0;
+    size_t w_off = 0;           // offset (in halfs) into the weight blob: layout [tap][cout][cin]
+    size_t b_off = 0;           // offset (in floats) into the bias blob
+    int stream = 0;             // branch stream the op runs on
+    int join_before = 0;        // all streams must have finished earlier ops before this op starts
+};
+
+struct UmmaPlan;                // conv_umma.cu: per-op tensor maps + tile shape (per batch size)
+
+struct HrnetModel {
+    int width = 32, in_h = 256, in_w = 192;
+    std::vector<HTensor> tensors;
+    std::vector<HOp> ops;
+    int n_bufs = 0;
+    std::vector<size_t> buf_elems_per_image;   // halfs per image for each buffer
+    size_t n_weights = 0, n_biases = 0;
+    __half* d_weights = nullptr;
+    float* d_bias = nullptr;
+    int engine = 0;             // 0 SIMT, 1 tcgen05 (falls back per-op where the shape is unsupported)
+    // per-batch-size execution state
+    int cap_P = 0;
+    std::vector<__half*> bufs;
+    std::vector<UmmaPlan*> umma;                // one per op (nullptr = SIMT)
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_P = 0, graph_dtype = -1, graph_engine = -1;
+    const void* graph_in = nullptr;
+    void* graph_out = nullptr;
+    uint64_t graph_nodes = 0;
+    cudaStream_t side[3] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+// builder (hrnet.cu)
+void hrnet_build_program(HrnetModel& m);
+
+// conv_umma.cu
+bool umma_supported(const HrnetModel& m, const HOp& op);
+int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int P, UmmaPlan** out);
+void umma_plan_destroy(UmmaPlan* p);
+int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* plan, int P, cudaStream_t st);

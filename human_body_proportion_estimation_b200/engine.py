@@ -1,0 +1,366 @@
+"""Per-GPU engine: a thin, numpy-facing layer over the C ABI (include/hbp.h).
+
+One `Engine` = one hbp_ctx = one GPU; it is the in-process replacement of the
+reference's Triton client (human_body_length_est/modules/triton_utils.py:11-34,
+131-177).  Host arrays in, host arrays out; every method is one C-ABI call.
+`MultiGpuEngine` shards frames across several engines with one Python thread
+per GPU (ctypes drops the GIL) -- frames are independent, so there is no
+collective anywhere on the path.
+"""
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _capi
+from ._capi import DEVICE, F16, F32, HOST, NCHW, NHWC, U8, check, ptr
+
+# person_det_pose_edet4_trtserver.py:62-63
+KEYPOINT_THRES_LIST = (0.45, 0.46, 0.45, 0.40, 0.34, 0.10, 0.10, 0.10, 0.10,
+                       0.24, 0.30, 0.11, 0.10, 0.15, 0.10, 0.25, 0.20)
+SEGMENT_KEYS = ("shoulder", "torso", "lshoulder_lelbow", "rshoulder_relbow", "lwrist_lelbow",
+                "rwrist_relbow", "rhip_lhip", "rhip_rknee", "lhip_lknee", "rankle_rknee",
+                "lankle_lknee")
+NOT_VISIBLE = "Part not visible"
+_NP2HBP = {np.dtype(np.uint8): U8, np.dtype(np.float16): F16, np.dtype(np.float32): F32}
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._lib = _capi.lib()
+        self._ctx = C.c_void_p()
+        check(self._lib.hbp_ctx_create(int(device), C.byref(self._ctx)))
+        self.device = int(device)
+        self.hrnet = None           # (width, in_h, in_w) once loaded
+
+    def close(self):
+        if self._ctx:
+            self._lib.hbp_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing --------------------------------------------------------
+    def sync(self):
+        check(self._lib.hbp_sync(self._ctx))
+
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        check(self._lib.hbp_dev_alloc(self._ctx, int(nbytes), C.byref(p)))
+        return p.value
+
+    def dev_free(self, p):
+        check(self._lib.hbp_dev_free(self._ctx, C.c_void_p(p)))
+
+    def pinned_empty(self, shape, dtype):
+        """numpy array backed by pinned host memory (freed with the engine)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        check(self._lib.hbp_host_alloc(self._ctx, max(n, 1), C.byref(p)))
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def h2d(self, dev_ptr, arr):
+        check(self._lib.hbp_copy_h2d(self._ctx, C.c_void_p(dev_ptr), ptr(arr), arr.nbytes))
+
+    def d2h(self, arr, dev_ptr):
+        check(self._lib.hbp_copy_d2h(self._ctx, ptr(arr), C.c_void_p(dev_ptr), arr.nbytes))
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        p = self.dev_alloc(arr.nbytes)
+        self.h2d(p, arr)
+        self.sync()
+        return p
+
+    def timer_start(self, slot=0):
+        check(self._lib.hbp_timer_start(self._ctx, slot))
+
+    def timer_stop(self, slot=0):
+        check(self._lib.hbp_timer_stop(self._ctx, slot))
+
+    def timer_ms(self, slot=0):
+        ms = C.c_float()
+        check(self._lib.hbp_timer_elapsed_ms(self._ctx, slot, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        check(self._lib.hbp_flush_l2(self._ctx))
+
+    def kernel_launches(self):
+        n = C.c_uint64()
+        check(self._lib.hbp_kernel_launches(self._ctx, C.byref(n)))
+        return n.value
+
+    # ---- K1 ----------------------------------------------------------------
+    def preprocess(self, frames, mode, out_h=None, out_w=None, swap_rb=True, pad_value=128,
+                   out_dtype=np.float32, layout=NCHW):
+        frames = _c(frames, np.uint8)
+        if frames.ndim == 3:
+            frames = frames[None]
+        n, h, w, _ = frames.shape
+        out_h, out_w = out_h or h, out_w or w
+        shape = (n, 3, out_h, out_w) if layout == NCHW else (n, out_h, out_w, 3)
+        out = np.empty(shape, out_dtype)
+        check(self._lib.hbp_preprocess(self._ctx, ptr(frames), n, h, w, mode, out_h, out_w, int(swap_rb),
+                                       pad_value, ptr(out), _NP2HBP[np.dtype(out_dtype)], layout, HOST))
+        return out
+
+    # ---- K2 / K3 -------------------------------------------------------------
+    def yolo_decode_raw(self, heads, in_w=640, in_h=640):
+        heads = [_c(h, np.float32) for h in heads]
+        B, nc = heads[0].shape[0], heads[0].shape[-1] - 5
+        S = [h.shape[2] for h in heads]
+        out = np.empty((B, 3 * sum(s * s for s in S), 5 + nc), np.float32)
+        check(self._lib.hbp_yolo_decode_raw(self._ctx, ptr(heads[0]), ptr(heads[1]), ptr(heads[2]), B,
+                                            S[0], S[1], S[2], nc, in_w, in_h, ptr(out), HOST))
+        return out
+
+    def yolo_nms(self, pred, conf_thres=0.25, iou_thres=0.45, classes=None, max_det=300):
+        pred = _c(pred, np.float32)
+        B, N, E = pred.shape
+        cls = _c(classes, np.int32) if classes is not None else None
+        det = np.zeros((B, max_det, 6), np.float32)
+        cnt = np.zeros((B,), np.int32)
+        check(self._lib.hbp_yolo_nms(self._ctx, ptr(pred), B, N, E - 5, float(conf_thres), float(iou_thres),
+                                     ptr(cls), 0 if cls is None else len(cls), max_det, ptr(det), ptr(cnt), HOST))
+        return [det[b, :cnt[b]].copy() for b in range(B)]
+
+    def yolo_nms_legacy(self, pred, num_classes, conf_thres=0.5, nms_thres=0.4, max_out=None):
+        pred = _c(pred, np.float32)
+        B, N, E = pred.shape
+        max_out = max_out or N
+        det = np.zeros((B, max_out, 7), np.float32)
+        cnt = np.zeros((B,), np.int32)
+        check(self._lib.hbp_yolo_nms_legacy(self._ctx, ptr(pred), B, N, num_classes, float(conf_thres),
+                                            float(nms_thres), max_out, ptr(det), ptr(cnt), HOST))
+        return [None if cnt[b] < 0 else det[b, :cnt[b]].copy() for b in range(B)]
+
+    def scale_coords(self, img1_shape, coords, img0_shape):
+        """in place on a float32 (n,>=4) array like the reference (onnx_utils.py:252-266)"""
+        box = _c(coords[:, :4], np.float32)
+        check(self._lib.hbp_scale_coords(self._ctx, ptr(box), box.shape[0], int(img1_shape[0]),
+                                         int(img1_shape[1]), int(img0_shape[0]), int(img0_shape[1]), HOST))
+        coords[:, :4] = box
+        return coords
+
+    def edet_person_filter(self, boxes, scores, classes, det_thres, x_expand, y_expand, img_h, img_w,
+                           max_persons=3, person_class=1.0):
+        boxes, scores, classes = _c(boxes, np.float32), _c(scores, np.float32), _c(classes, np.float32)
+        if boxes.ndim == 2:
+            boxes, scores, classes = boxes[None], scores[None], classes[None]
+        F_, K = scores.shape
+        out = np.zeros((F_, max_persons, 4), np.float32)
+        cnt = np.zeros((F_,), np.int32)
+        check(self._lib.hbp_edet_person_filter(self._ctx, ptr(boxes), ptr(scores), ptr(classes), F_, K,
+                                               float(person_class), float(det_thres), float(x_expand),
+                                               float(y_expand), img_h, img_w, max_persons, ptr(out), ptr(cnt), HOST))
+        return [out[f, :cnt[f]].copy() for f in range(F_)]
+
+    # ---- K4 ----------------------------------------------------------------
+    def crop_warp(self, frames, mats, frame_idx, out_h, out_w, swap_rb=True, out_dtype=np.float16):
+        frames = _c(frames, np.uint8)
+        if frames.ndim == 3:
+            frames = frames[None]
+        mats = _c(mats, np.float64).reshape(-1, 6)
+        fi = _c(frame_idx, np.int32)
+        P = mats.shape[0]
+        out = np.empty((P, 3, out_h, out_w), out_dtype)
+        check(self._lib.hbp_crop_warp(self._ctx, ptr(frames), frames.shape[0], frames.shape[1],
+                                      frames.shape[2], ptr(mats), ptr(fi), P, out_h, out_w, int(swap_rb),
+                                      ptr(out), _NP2HBP[np.dtype(out_dtype)], HOST))
+        return out
+
+    # ---- K5 ----------------------------------------------------------------
+    def load_hrnet(self, weights=None, width=32, in_h=256, in_w=192, seed=0):
+        from . import hrnet_arch
+        if weights is None:
+            weights = hrnet_arch.random_weights(width, in_h, in_w, seed)
+        wb, bb = hrnet_arch.pack(weights, width, in_h, in_w)
+        check(self._lib.hbp_hrnet_load(self._ctx, width, in_h, in_w, ptr(wb), wb.size, ptr(bb), bb.size))
+        self.hrnet = (width, in_h, in_w)
+        return weights
+
+    def conv2d_nhwc(self, x, w, bias, residual=None, stride=1, up=1, relu=False, engine=1):
+        """x (P,H,W,Cin) f16, w (Cout,Cin,k,k) -> (P,H/stride*up,W/stride*up,Cout) f16, used_engine"""
+        x = _c(x, np.float16)
+        P, H, W, Cin = x.shape
+        Cout, _, k, _ = w.shape
+        wb = _c(np.transpose(np.asarray(w), (2, 3, 0, 1)), np.float16)
+        b = _c(bias, np.float32)
+        out = np.empty((P, H // stride * up, W // stride * up, Cout), np.float16)
+        r = _c(residual, np.float16) if residual is not None else None
+        used = C.c_int(-1)
+        check(self._lib.hbp_conv2d_nhwc(self._ctx, int(engine), ptr(x), P, H, W, Cin, ptr(wb), ptr(b), ptr(r),
+                                        Cout, k, stride, up, int(relu), ptr(out), C.byref(used), HOST))
+        return out, used.value
+
+    def set_hrnet_engine(self, engine):
+        check(self._lib.hbp_hrnet_set_engine(self._ctx, int(engine)))
+
+    def hrnet_forward(self, crops, out_dtype=np.float32):
+        crops = _c(crops, np.float16)
+        P = crops.shape[0]
+        _, ih, iw = self.hrnet
+        assert crops.shape[1:] == (3, ih, iw), crops.shape
+        hm = np.empty((P, 17, ih // 4, iw // 4), out_dtype)
+        check(self._lib.hbp_hrnet_forward(self._ctx, ptr(crops), P, ptr(hm), _NP2HBP[np.dtype(out_dtype)], HOST))
+        return hm
+
+    # ---- K6 ----------------------------------------------------------------
+    def decode_proportions(self, heatmaps, boxes_yxyx_px=None, height_cm=None,
+                           joint_thr=KEYPOINT_THRES_LIST, quarter_offset=False):
+        hm = np.ascontiguousarray(heatmaps)
+        if hm.dtype not in (np.float32, np.float16):
+            hm = hm.astype(np.float32)
+        P, J, Hh, Wh = hm.shape
+        out = dict(kpts_hm=np.zeros((P, J, 2), np.float32), scores=np.zeros((P, J), np.float32),
+                   argmax=np.zeros((P, J), np.int32))
+        boxes = hcm = thr = None
+        if boxes_yxyx_px is not None:
+            boxes = _c(boxes_yxyx_px, np.float32).reshape(P, 4)
+            hcm = _c(np.broadcast_to(np.asarray(height_cm, np.float64), (P,)), np.float64)
+            thr = _c(joint_thr, np.float32)
+            out.update(kpts_img=np.zeros((P, J, 2), np.float32), ignored=np.zeros((P,), np.uint32))
+            if J == 17:
+                out.update(lengths_cm=np.zeros((P, 11), np.float32), torso_cm=np.zeros((P,), np.float64))
+        check(self._lib.hbp_decode_proportions(
+            self._ctx, ptr(hm), _NP2HBP[hm.dtype], P, J, Hh, Wh, ptr(boxes), ptr(hcm), ptr(thr),
+            int(quarter_offset), ptr(out["kpts_hm"]), ptr(out.get("kpts_img")), ptr(out["scores"]),
+            ptr(out["argmax"]), ptr(out.get("ignored")), ptr(out.get("lengths_cm")), ptr(out.get("torso_cm")),
+            HOST))
+        return out
+
+    # ---- fused pipeline --------------------------------------------------------
+    def pose_pipeline(self, frames, mats, frame_idx, boxes_yxyx_px, height_cm,
+                      joint_thr=KEYPOINT_THRES_LIST, swap_rb=True, quarter_offset=False,
+                      return_heatmaps=None):
+        """frames (n,h,w,3) u8 + per-person 2x3 matrices/boxes -> keypoints, scores, lengths.
+        return_heatmaps: None | np.float16 | np.float32."""
+        frames = _c(frames, np.uint8)
+        if frames.ndim == 3:
+            frames = frames[None]
+        mats = _c(mats, np.float64).reshape(-1, 6)
+        P = mats.shape[0]
+        fi = _c(frame_idx, np.int32)
+        boxes = _c(boxes_yxyx_px, np.float32).reshape(P, 4)
+        hcm = _c(np.broadcast_to(np.asarray(height_cm, np.float64), (P,)), np.float64)
+        thr = _c(joint_thr, np.float32)
+        _, ih, iw = self.hrnet
+        out = dict(kpts_img=np.zeros((P, 17, 2), np.float32), scores=np.zeros((P, 17), np.float32),
+                   ignored=np.zeros((P,), np.uint32), lengths_cm=np.zeros((P, 11), np.float32),
+                   torso_cm=np.zeros((P,), np.float64))
+        hm = None
+        prm = _capi.PipelineParams(frames.shape[0], frames.shape[1], frames.shape[2], P, int(swap_rb),
+                                   int(quarter_offset), F32)
+        if return_heatmaps is not None:
+            hm = np.empty((P, 17, ih // 4, iw // 4), return_heatmaps)
+            prm.heatmap_dtype = _NP2HBP[np.dtype(return_heatmaps)]
+        check(self._lib.hbp_pose_pipeline(self._ctx, C.byref(prm), ptr(frames), ptr(mats), ptr(fi), ptr(boxes),
+                                          ptr(hcm), ptr(thr), ptr(out["kpts_img"]), ptr(out["scores"]),
+                                          ptr(out["ignored"]), ptr(out["lengths_cm"]), ptr(out["torso_cm"]),
+                                          ptr(hm)))
+        if hm is not None:
+            out["heatmaps"] = hm
+        return out
+
+
+def lengths_to_dict(lengths_row, torso):
+    """(11,) float32 + float64 torso -> the reference's dict
+    (pose_estimator.py:191-200): np.float32 values, np.float64 torso, or the
+    string "Part not visible" for 0."""
+    d = {}
+    for k, key in enumerate(SEGMENT_KEYS):
+        v = lengths_row[k]
+        if key == "torso":
+            d[key] = np.float64(torso) if torso > 0 else NOT_VISIBLE
+        else:
+            d[key] = np.float32(v) if v > 0 else NOT_VISIBLE
+    return d
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_engine(device=0):
+    with _default_lock:
+        if device not in _default:
+            _default[device] = Engine(device)
+        return _default[device]
+
+
+class MultiGpuEngine:
+    """Frame-level data parallelism over the GPUs of one box:
+    unit = frame (+ its persons); frame f -> GPU f mod G; results concatenated
+    on the host in frame order.  No collective, no peer traffic."""
+
+    def __init__(self, devices=None, **hrnet_kw):
+        if devices is None:
+            n = C.c_int()
+            check(_capi.lib().hbp_device_count(C.byref(n)))
+            devices = list(range(n.value))
+        self.engines = [Engine(d) for d in devices]
+        self._hrnet_kw = hrnet_kw
+        weights = None
+        for e in self.engines:
+            weights = e.load_hrnet(weights=weights, **hrnet_kw)
+
+    @staticmethod
+    def shard(n_frames, n_ranks):
+        """frame indices per rank (round robin)"""
+        return [list(range(r, n_frames, n_ranks)) for r in range(n_ranks)]
+
+    def pose_pipeline(self, frames, mats, frame_idx, boxes_yxyx_px, height_cm, **kw):
+        frames = np.asarray(frames)
+        frame_idx = np.asarray(frame_idx, np.int32)
+        mats = np.asarray(mats, np.float64).reshape(-1, 6)
+        boxes = np.asarray(boxes_yxyx_px, np.float32).reshape(-1, 4)
+        hcm = np.broadcast_to(np.asarray(height_cm, np.float64), (mats.shape[0],))
+        G = len(self.engines)
+        plan = self.shard(frames.shape[0], G)
+        results = [None] * G
+        errors = []
+
+        def work(r):
+            try:
+                fr = plan[r]
+                if not fr:
+                    return
+                remap = {f: i for i, f in enumerate(fr)}
+                sel = np.nonzero(np.isin(frame_idx, fr))[0]
+                if sel.size == 0:
+                    return
+                local_idx = np.array([remap[f] for f in frame_idx[sel]], np.int32)
+                out = self.engines[r].pose_pipeline(frames[fr], mats[sel], local_idx, boxes[sel], hcm[sel], **kw)
+                results[r] = (sel, out)
+            except Exception as exc:      # surfaced after the join
+                errors.append(exc)
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(G)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        merged = None
+        P = mats.shape[0]
+        for item in results:
+            if item is None:
+                continue
+            sel, out = item
+            if merged is None:
+                merged = {k: np.zeros((P,) + v.shape[1:], v.dtype) for k, v in out.items()}
+            for k, v in out.items():
+                merged[k][sel] = v
+        return merged

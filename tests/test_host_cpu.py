@@ -1,0 +1,115 @@
+"""CPU tier: the C-ABI library loads and exports what include/hbp.h declares (no
+compute without a GPU), host-side logic (program builder, weight packing, frame
+sharding, crop geometry), and loud failure without a device."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from human_body_proportion_estimation_b200 import build, _capi
+    build.build()
+    return _capi.lib()
+
+
+def test_header_symbols_exported(lib):
+    from human_body_proportion_estimation_b200 import _capi
+    hdr = open(os.path.join(ROOT, "include", "hbp.h")).read()
+    declared = set(re.findall(r"HBP_API\s+[\w\s\*]+?\b(hbp_\w+)\s*\(", hdr))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_capi.EXPORTS)         # the ctypes table binds exactly the header
+    assert lib.hbp_version() == 100
+
+
+def test_no_gpu_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from human_body_proportion_estimation_b200 import _capi
+    from human_body_proportion_estimation_b200.engine import Engine
+    with pytest.raises(_capi.HbpError, match="no CPU fallback"):
+        Engine(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "human_body_proportion_estimation_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_hrnet_program(lib):
+    from human_body_proportion_estimation_b200 import hrnet_arch
+    rows, nw, nb = hrnet_arch.layer_table(32, 256, 192)
+    assert len(rows) == 293 and nw == 28481760        # 28.48 M conv parameters (paper: 28.5 M)
+    rows48, nw48, _ = hrnet_arch.layer_table(48, 384, 288)
+    assert len(rows48) == 293 and nw48 == 63516144    # 63.5 M (paper: 63.6 M)
+    names = [r[0] for r in rows]
+    assert len(set(names)) == len(names)
+    for key in ("conv1", "layer1.0.downsample.0", "transition1.1.0.0", "stage2.0.branches.1.3.conv2",
+                "stage3.3.fuse_layers.2.0.1.0", "stage4.2.fuse_layers.0.3.0", "transition3.3.0.0", "final_layer"):
+        assert key in names, key
+    assert not any(n.startswith("stage4.2.fuse_layers.1") for n in names)   # last module fuses to branch 0 only
+    # offsets are contiguous in table order
+    off = 0
+    for name, cin, cout, k, s, w_off, b_off in rows:
+        assert w_off == off
+        off += cin * cout * k * k
+    w = hrnet_arch.random_weights(32, 256, 192, seed=0)
+    wb, bb = hrnet_arch.pack(w)
+    assert wb.dtype == np.float16 and wb.size == nw and bb.size == nb
+    name, cin, cout, k, s, w_off, _ = rows[1]
+    assert np.array_equal(wb[w_off:w_off + 64], w[name][0][0, :, 0, 0].astype(np.float16))   # [tap][cout][cin]
+
+
+def test_oracle_hrnet_matches_independent_torch_modules(lib):
+    """the functional fp32 oracle equals an nn.Module-free recomputation of one block"""
+    import torch
+    import torch.nn.functional as F
+    from human_body_proportion_estimation_b200 import hrnet_arch
+    from oracle.hrnet_fp32 import HRNetFP32
+    w = hrnet_arch.random_weights(32, 64, 64, seed=3)
+    net = HRNetFP32(w, 32)
+    x = torch.rand(1, 3, 64, 64)
+    hm = net(x)
+    assert hm.shape == (1, 17, 16, 16) and torch.isfinite(hm).all()
+    t = F.relu(F.conv2d(x, torch.from_numpy(w["conv1"][0]), torch.from_numpy(w["conv1"][1]), stride=2, padding=1))
+    assert torch.allclose(net.cv("conv1", x, stride=2), t)
+
+
+def test_frame_sharding_and_geometry():
+    from human_body_proportion_estimation_b200.engine import MultiGpuEngine, lengths_to_dict
+    from human_body_proportion_estimation_b200 import geometry
+    plan = MultiGpuEngine.shard(10, 4)
+    assert plan == [[0, 4, 8], [1, 5, 9], [2, 6], [3, 7]]
+    assert sorted(sum(plan, [])) == list(range(10))
+    from oracle import imgproc
+    box = np.array([0.1, 0.2, 0.8, 0.5], np.float32)
+    assert np.array_equal(geometry.crop_and_resize_matrices(box, 1080, 1920, 384, 288)[0],
+                          imgproc.crop_and_resize_matrix(box, 1080, 1920, 384, 288))
+    assert np.array_equal(geometry.box_resize_matrices([10, 20, 110, 220], 256, 192)[0],
+                          imgproc.box_resize_matrix([10, 20, 110, 220], 256, 192))
+    d = lengths_to_dict(np.array([1.5, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0], np.float32), 3.25)
+    assert d["shoulder"] == np.float32(1.5) and isinstance(d["torso"], np.float64)
+    assert d["lankle_lknee"] == "Part not visible"
+
+
+def test_host_length_helper_matches_reference_values():
+    from human_body_proportion_estimation_b200.pose_estimator import PoseEstimator
+    from oracle import geometry as og
+    rng = np.random.default_rng(1)
+    k = rng.uniform(0, 800, (17, 2)).astype(np.float32)
+    for ign in (set(), {0, 9}, {5}, {11, 13}):
+        a = PoseEstimator.get_keypoint_dist_dict(0.41, k, ign)
+        b = og.lengths_dict(0.41, k, ign)
+        assert a == b
+    with pytest.raises(UnboundLocalError):
+        PoseEstimator.get_keypoint_dist_dict(0.41, k, {5}, strict=True)
