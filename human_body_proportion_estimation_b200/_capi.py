@@ -108,8 +108,9 @@ def ptr(a):
     return C.c_void_p(a.ctypes.data)
 
 
-def describe_hrnet(width, in_h, in_w):
-    """[(name, cin, cout, k, stride, w_off, b_off)], n_weights, n_biases -- host only."""
+def describe_hrnet(width, in_h, in_w, full=False):
+    """[(name, cin, cout, k, stride, w_off, b_off)], n_weights, n_biases -- host only.
+    full=True appends (out_h, out_w, up) to every row."""
     l = lib()
     nw, nb, need = C.c_size_t(), C.c_size_t(), C.c_size_t()
     st = l.hbp_hrnet_describe(width, in_h, in_w, None, 0, C.byref(nw), C.byref(nb), C.byref(need))
@@ -119,5 +120,6 @@ def describe_hrnet(width, in_h, in_w):
     rows = []
     for line in buf.value.decode().splitlines():
         f = line.split()
-        rows.append((f[0], int(f[1]), int(f[2]), int(f[3]), int(f[4]), int(f[5]), int(f[6])))
+        row = (f[0], int(f[1]), int(f[2]), int(f[3]), int(f[4]), int(f[5]), int(f[6]))
+        rows.append(row + (int(f[7]), int(f[8]), int(f[9])) if full else row)
     return rows, nw.value, nb.value

@@ -663,7 +663,7 @@ int hrnet_single_conv(hbp_ctx* ctx, int engine, const __half* in, int P, int H, 
 }
 
 // host-only description of the program (no context needed): one line per conv
-//   name cin cout k stride w_off b_off
+//   name cin cout k stride w_off b_off out_h out_w up   (out_h/out_w before the fused upsample)
 extern "C" int hbp_hrnet_describe(int width, int in_h, int in_w, char* buf, size_t buf_bytes,
                                           size_t* n_weights, size_t* n_biases, size_t* needed) {
     if ((width != 32 && width != 48) || in_h % 32 || in_w % 32 || in_h <= 0 || in_w <= 0) {
@@ -676,8 +676,11 @@ extern "C" int hbp_hrnet_describe(int width, int in_h, int in_w, char* buf, size
     std::string s;
     char line[256];
     for (const HOp& op : m.ops) {
-        snprintf(line, sizeof(line), "%s %d %d %d %d %zu %zu\n", op.name.c_str(), op.cin, op.cout, op.k,
-                 op.stride, op.w_off, op.b_off);
+        int ho = 0, wo = 0;
+        if (op.kind == OP_STEM1) { ho = m.in_h / 2; wo = m.in_w / 2; }
+        else { ho = m.tensors[op.in].h / op.stride; wo = m.tensors[op.in].w / op.stride; }
+        snprintf(line, sizeof(line), "%s %d %d %d %d %zu %zu %d %d %d\n", op.name.c_str(), op.cin, op.cout, op.k,
+                 op.stride, op.w_off, op.b_off, ho, wo, op.up);
         s += line;
     }
     if (n_weights) *n_weights = m.n_weights;

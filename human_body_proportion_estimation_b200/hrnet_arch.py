@@ -86,3 +86,16 @@ def from_state_dict(sd, width=32, in_h=256, in_w=192, eps=1e-5):
         s = g / np.sqrt(var + eps)
         out[name] = (w * s[:, None, None, None], beta - mu * s)
     return out
+
+
+def flops_per_crop(width=32, in_h=256, in_w=192):
+    """2 x MACs over all 293 convolutions of one forward (the algorithmic FLOP figure
+    the roofline uses), and the per-shape-class breakdown {(cin,cout,k,stride,ho,wo): flops}."""
+    rows, _, _ = _capi.describe_hrnet(width, in_h, in_w, full=True)
+    total, classes = 0, {}
+    for name, cin, cout, k, stride, _, _, ho, wo, up in rows:
+        f = 2 * cin * cout * k * k * ho * wo
+        total += f
+        key = (cin, cout, k, stride, ho, wo)
+        classes[key] = classes.get(key, 0) + f
+    return total, classes

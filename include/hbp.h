@@ -166,7 +166,8 @@ HBP_API int hbp_hrnet_load(hbp_ctx* ctx, int width, int in_h, int in_w,
                    const float* biases_f32, size_t n_biases);
 /* Host-only (no context, no GPU): the conv program of an architecture as text,
  * one line per convolution in weight-blob order:
- *   "<public HRNet state_dict prefix> <cin> <cout> <k> <stride> <w_off> <b_off>\n"
+ *   "<public HRNet state_dict prefix> <cin> <cout> <k> <stride> <w_off> <b_off> <out_h> <out_w> <up>\n"
+ * (out_h,out_w = conv output size before the fused nearest upsample x<up>)
  * weights of a conv are [tap][cout][cin] halfs at w_off, biases floats at b_off.
  * *needed = bytes required for buf (incl. NUL). */
 HBP_API int hbp_hrnet_describe(int width, int in_h, int in_w, char* buf, size_t buf_bytes,
