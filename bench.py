@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Benchmark of the top-down pose hot path (BASELINE.json metric: person crops/sec
+through det -> crop -> HRNet -> decode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] -- HRNet-W32 256x192 fp16 on 64
+synthetic person crops from one 1080p frame per step and per GPU.  One step =
+crop (K4) -> HRNet (K5, 293 launches in one CUDA graph) -> decode + proportions (K6).
+The detector-head stages (K1 letterbox, K2/K3 NMS) are timed beside it on the
+configs[2] shapes and reported under "stages_ms" (they do not gate the crops).
+
+  value     crops/s with the frame and parameters resident in HBM, device-timed with
+            CUDA events on the library's stream, L2 flushed between steps
+  e2e       crops/s through the public API (Engine.pose_pipeline) with HOST buffers:
+            pinned-host frame -> H2D -> crop -> HRNet -> decode -> D2H of the results
+  roofline  HRNet conv stack: algorithmic FLOPs (2 x MACs of the 293 convs x 64 crops)
+            / CUDA-event time of the HRNet stage inside the timed steps, against the
+            measured sustained bf16 peak of MEASURED_PEAKS.json
+  cpu_baseline / --impl reference
+            the reference's CPU path on the box's host cores: cv2.warpAffine crops,
+            torch fp32 HRNet (stand-in for onnxruntime, which is not installable
+            offline) and the oracle's per-person decode loop, on a bounded sample
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CROPS_PER_FRAME = 64
+FRAME_H, FRAME_W = 1080, 1920
+WIDTH, IN_H, IN_W = 32, 256, 192
+METRIC = "person crops/sec (det->crop->HRNet->decode)"
+UNIT = "crops/s"
+
+
+def workload():
+    from human_body_proportion_estimation_b200 import geometry, synth
+    frame = synth.frame_u8(FRAME_H, FRAME_W, seed=synth.SEED_BASE + 2)
+    boxes = synth.person_boxes_yxyx_px(CROPS_PER_FRAME, FRAME_H, FRAME_W, seed=synth.SEED_BASE + 2,
+                                       hmin=150, hmax=900)
+    boxes_n = boxes / np.array([FRAME_H, FRAME_W, FRAME_H, FRAME_W], np.float32)
+    mats = geometry.crop_and_resize_matrices(boxes_n, FRAME_H, FRAME_W, IN_H, IN_W)
+    return frame, boxes, mats
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get("bf16_tflops_sustained", d.get("bf16_tflops")), hbm=d.get("hbm_gbs"),
+                    src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.lines = None, []
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline
+# --------------------------------------------------------------------------
+def cpu_reference_run(n_crops, steps, warmup, weights=None):
+    """The reference's CPU path on `n_crops` crops of the workload per step.  Returns
+    (crops_per_s, ms_per_step, cores, note)."""
+    import torch
+    from human_body_proportion_estimation_b200 import hrnet_arch
+    from oracle import geometry as og
+    from oracle.hrnet_fp32 import HRNetFP32
+    try:
+        import cv2
+        have_cv2 = True
+    except Exception:
+        have_cv2 = False
+        from oracle import imgproc
+    frame, boxes, mats = workload()
+    if weights is None:
+        weights = hrnet_arch.random_weights(WIDTH, IN_H, IN_W, seed=0)
+    net = HRNetFP32(weights, WIDTH)
+    cores = torch.get_num_threads()
+    if have_cv2:
+        cv2.setNumThreads(cores)
+
+    def step():
+        crops = []
+        for p in range(n_crops):
+            if have_cv2:      # the north-star crop gate: cv2.warpAffine on the u8 frame
+                c = cv2.warpAffine(frame, mats[p], (IN_W, IN_H), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP,
+                                   borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+                c = cv2.cvtColor(c, cv2.COLOR_BGR2RGB)
+                crops.append(np.transpose(c / 255.0, (2, 0, 1)).astype(np.float32))
+            else:
+                crops.append(imgproc.crop_persons(frame, [mats[p]], IN_H, IN_W, True, np.float32)[0])
+        hm = net(np.stack(crops)).numpy()                      # torch fp32, all host threads
+        out = []
+        for p in range(n_crops):                                # reference's per-person python loop
+            out.append(og.person_postprocess(hm[p], boxes[p], 175)["lengths"])
+        return out
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    note = ("%d of the %d crops of one 1080p frame per step: %s crop, torch-fp32 HRNet-W32 (stand-in for "
+            "onnxruntime CPU), oracle decode loop" % (n_crops, CROPS_PER_FRAME,
+                                                      "cv2.warpAffine" if have_cv2 else "numpy cv2-exact"))
+    return n_crops * steps / dt, dt / steps * 1e3, cores, note
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n = 8
+    val, ms, cores, note = cpu_reference_run(n, max(1, args.steps), max(0, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": note},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict():
+    return {"workload": "configs[1]: HRNet-W32 256x192 fp16, 64 synthetic person crops from one 1080p frame "
+                        "per step per GPU (crop -> HRNet -> decode+proportions)",
+            "frame": [FRAME_H, FRAME_W, 3], "crops_per_step_per_gpu": CROPS_PER_FRAME,
+            "hrnet": "W%d %dx%d" % (WIDTH, IN_H, IN_W), "weights": "random-init (seed 0), BN folded",
+            "l2": "flushed between timed steps (256 MiB write)", "parallelism": "frame-sharded, no collective"}
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import ctypes as C
+    from human_body_proportion_estimation_b200 import _capi, hrnet_arch, synth
+    from human_body_proportion_estimation_b200.engine import Engine, KEYPOINT_THRES_LIST
+    from human_body_proportion_estimation_b200._capi import DEVICE, F16, F32, NCHW, PRE_LETTERBOX, check, ptr
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    eng = Engine(local_rank)
+    lib = eng._lib
+    ctx = eng._ctx
+    weights = eng.load_hrnet(None, WIDTH, IN_H, IN_W, seed=0)
+    frame, boxes, mats = workload()
+    P = CROPS_PER_FRAME
+    Hh, Wh = IN_H // 4, IN_W // 4
+
+    # ---- device-resident buffers for `value`
+    d_frame = eng.to_device(frame)
+    d_mats = eng.to_device(mats.reshape(P, 6))
+    d_fi = eng.to_device(np.zeros(P, np.int32))
+    d_boxes = eng.to_device(boxes)
+    d_hcm = eng.to_device(np.full(P, 175.0))
+    d_thr = eng.to_device(np.asarray(KEYPOINT_THRES_LIST, np.float32))
+    d_crops = eng.dev_alloc(P * 3 * IN_H * IN_W * 2)
+    d_hm = eng.dev_alloc(P * 17 * Hh * Wh * 2)
+    d_kp = eng.dev_alloc(P * 17 * 2 * 4)
+    d_sc = eng.dev_alloc(P * 17 * 4)
+    d_ig = eng.dev_alloc(P * 4)
+    d_len = eng.dev_alloc(P * 11 * 4)
+    d_to = eng.dev_alloc(P * 8)
+
+    def step_device(time_hrnet=False):
+        check(lib.hbp_crop_warp(ctx, C.c_void_p(d_frame), 1, FRAME_H, FRAME_W, C.c_void_p(d_mats), C.c_void_p(d_fi),
+                                P, IN_H, IN_W, 1, C.c_void_p(d_crops), F16, DEVICE))
+        if time_hrnet:
+            eng.timer_start(1)
+        check(lib.hbp_hrnet_forward(ctx, C.c_void_p(d_crops), P, C.c_void_p(d_hm), F16, DEVICE))
+        if time_hrnet:
+            eng.timer_stop(1)
+        check(lib.hbp_decode_proportions(ctx, C.c_void_p(d_hm), F16, P, 17, Hh, Wh, C.c_void_p(d_boxes),
+                                         C.c_void_p(d_hcm), C.c_void_p(d_thr), 0, None, C.c_void_p(d_kp),
+                                         C.c_void_p(d_sc), None, C.c_void_p(d_ig), C.c_void_p(d_len),
+                                         C.c_void_p(d_to), DEVICE))
+
+    for _ in range(max(args.warmup, 3)):          # >= 3 warm-up steps; the 2nd captures the CUDA graph
+        step_device()
+    eng.sync()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    eng.sync()
+    launches0 = eng.kernel_launches()
+    step_ms, hrnet_ms = [], []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.flush_l2()
+        eng.timer_start(0)
+        step_device(time_hrnet=True)
+        eng.timer_stop(0)
+        step_ms.append(eng.timer_ms(0))
+        hrnet_ms.append(eng.timer_ms(1))
+    eng.sync()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    launches = eng.kernel_launches() - launches0
+    dev_ms_total = sum(step_ms)
+
+    # ---- e2e through the public API with host buffers
+    h_frame = eng.pinned_empty(frame.shape, np.uint8)
+    h_frame[...] = frame
+    for _ in range(3):
+        out = eng.pose_pipeline(h_frame, mats, np.zeros(P, np.int32), boxes, 175)
+    barrier()
+    lat = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        t1 = time.perf_counter()
+        out = eng.pose_pipeline(h_frame, mats, np.zeros(P, np.int32), boxes, 175)
+        lat.append((time.perf_counter() - t1) * 1e3)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    h2d = frame.nbytes + P * (48 + 8 + 16 + 4) + 32 * 4
+    d2h = sum(v.nbytes for v in out.values())
+    clocks = sampler.stop() if sampler else None
+
+    # ---- max over ranks
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_ms_total, e2e_s, wall_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms_total, e2e_s, wall_ms = (float(x) for x in t.tolist())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-stage timings on the detector-head shapes (configs[2]), device-resident
+    stages = {}
+    try:
+        pred, _ = synth.yolo_decoded_head()
+        d_pred = eng.to_device(pred)
+        d_det = eng.dev_alloc(300 * 6 * 4)
+        d_cnt = eng.dev_alloc(4)
+        d_cls = eng.to_device(np.zeros(1, np.int32))
+        d_lb = eng.dev_alloc(3 * 640 * 640 * 2)
+
+        def timed(fn, reps=20):
+            fn(); eng.sync()
+            eng.timer_start(2)
+            for _ in range(reps):
+                fn()
+            eng.timer_stop(2)
+            return eng.timer_ms(2) / reps
+
+        stages["letterbox_1080p_to_640_f16"] = timed(lambda: check(lib.hbp_preprocess(
+            ctx, C.c_void_p(d_frame), 1, FRAME_H, FRAME_W, PRE_LETTERBOX, 640, 640, 1, 128, C.c_void_p(d_lb), F16, NCHW, DEVICE)))
+        stages["yolo_nms_25200x85_person"] = timed(lambda: check(lib.hbp_yolo_nms(
+            ctx, C.c_void_p(d_pred), 1, 25200, 80, 0.4, 0.5, C.c_void_p(d_cls), 1, 300, C.c_void_p(d_det), C.c_void_p(d_cnt), DEVICE)))
+        stages["crop_64x256x192_f16"] = timed(lambda: check(lib.hbp_crop_warp(
+            ctx, C.c_void_p(d_frame), 1, FRAME_H, FRAME_W, C.c_void_p(d_mats), C.c_void_p(d_fi), P, IN_H, IN_W, 1,
+            C.c_void_p(d_crops), F16, DEVICE)))
+        stages["decode_proportions_64x17x64x48_f16"] = timed(lambda: check(lib.hbp_decode_proportions(
+            ctx, C.c_void_p(d_hm), F16, P, 17, Hh, Wh, C.c_void_p(d_boxes), C.c_void_p(d_hcm), C.c_void_p(d_thr), 0,
+            None, C.c_void_p(d_kp), C.c_void_p(d_sc), None, C.c_void_p(d_ig), C.c_void_p(d_len), C.c_void_p(d_to), DEVICE)))
+        stages["hrnet_w32_64crops"] = statistics.mean(hrnet_ms)
+    except Exception as e:           # stage timings are informational
+        stages["error"] = str(e)
+
+    pk = peaks()
+    flops_crop, _ = hrnet_arch.flops_per_crop(WIDTH, IN_H, IN_W)
+    hr_ms = statistics.mean(hrnet_ms)
+    achieved = flops_crop * P / (hr_ms * 1e-3) / 1e12
+    n_conv_launch = 293
+    value = world * P * args.steps / (dev_ms_total * 1e-3)
+    e2e_val = world * P * args.steps / e2e_s
+
+    cpu = None
+    if world == 1 or True:
+        try:
+            cv, cms, cores, note = cpu_reference_run(8, 2, 1, weights)
+            cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port", "sample": note + "; 2 timed steps"}
+        except Exception as e:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": config_dict(),
+        "wall_ms_per_step": wall_ms / args.steps,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "p50_frame_latency_ms": statistics.median(lat), "api": "Engine.pose_pipeline (hbp_pose_pipeline)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "HRNet conv stack (conv_umma_kernel x%d + stem/head)" % (n_conv_launch - 2),
+                     "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                     "peak_source": pk["src"], "traffic": None,
+                     "flop_per_launch_avg": flops_crop * P / n_conv_launch,
+                     "launch_ms_avg": hr_ms / n_conv_launch, "hrnet_ms": hr_ms},
+        "cpu_baseline": cpu,
+        "stages_ms": stages,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # not under torchrun: relaunch one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
