@@ -63,6 +63,8 @@ _SIGS = {
     "hbp_hrnet_load": (_I, [_P, _I, _I, _I, _P, C.c_size_t, _P, C.c_size_t]),
     "hbp_hrnet_forward": (_I, [_P, _P, _I, _P, _I, _I]),
     "hbp_conv2d_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, C.POINTER(_I), _I]),
+    "hbp_conv2d_nhwc_timed": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, C.POINTER(_I), _I, _I,
+                                   C.POINTER(C.c_float)]),
     "hbp_hrnet_set_engine": (_I, [_P, _I]),
     "hbp_hrnet_debug_tensor": (_I, [_P, _I, _P, C.c_size_t, C.POINTER(_I), C.POINTER(_I),
                                     C.POINTER(_I), C.POINTER(_I)]),

@@ -314,9 +314,30 @@ int hbp_hrnet_load(hbp_ctx* ctx, int width, int in_h, int in_w, const void* w16,
     return hrnet_load(ctx, width, in_h, in_w, w16, nw, bias, nb);
 }
 
+static int conv2d_impl(hbp_ctx* ctx, int engine, const void* in, int P, int H, int W, int Cin, const void* weights,
+                       const float* bias, const void* residual, int Cout, int k, int stride, int up, int relu,
+                       void* out, int* used_engine, int mem, int iters, float* avg_ms);
+
 int hbp_conv2d_nhwc(hbp_ctx* ctx, int engine, const void* in, int P, int H, int W, int Cin, const void* weights,
                     const float* bias, const void* residual, int Cout, int k, int stride, int up, int relu,
                     void* out, int* used_engine, int mem) {
+    return conv2d_impl(ctx, engine, in, P, H, W, Cin, weights, bias, residual, Cout, k, stride, up, relu, out,
+                       used_engine, mem, 0, nullptr);
+}
+
+int hbp_conv2d_nhwc_timed(hbp_ctx* ctx, int engine, const void* in, int P, int H, int W, int Cin, const void* weights,
+                          const float* bias, const void* residual, int Cout, int k, int stride, int up, int relu,
+                          void* out, int* used_engine, int mem, int iters, float* avg_ms) {
+    HBP_REQUIRE(iters > 0 && avg_ms, "iters > 0 and avg_ms required");
+    return conv2d_impl(ctx, engine, in, P, H, W, Cin, weights, bias, residual, Cout, k, stride, up, relu, out,
+                       used_engine, mem, iters, avg_ms);
+}
+
+}  // extern "C"
+
+static int conv2d_impl(hbp_ctx* ctx, int engine, const void* in, int P, int H, int W, int Cin, const void* weights,
+                       const float* bias, const void* residual, int Cout, int k, int stride, int up, int relu,
+                       void* out, int* used_engine, int mem, int iters, float* avg_ms) {
     BIND(ctx);
     HBP_REQUIRE(in && weights && bias && out && P > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "bad shape");
     HBP_REQUIRE((k == 1 || k == 3) && (stride == 1 || stride == 2) && up >= 1 && Cin % 8 == 0 && Cout % 4 == 0, "unsupported conv");
@@ -330,11 +351,14 @@ int hbp_conv2d_nhwc(hbp_ctx* ctx, int engine, const void* in, int P, int H, int 
     const __half* d_r = st.in((const __half*)residual, n_out, SC_IN3);
     __half* d_o = st.out((__half*)out, n_out, SC_OUT0);
     if (st.status) return st.status;
-    int s = hrnet_single_conv(ctx, engine, d_in, P, H, W, Cin, d_w, d_b, d_r, Cout, k, stride, up, relu, d_o, used_engine);
+    int s = hrnet_single_conv(ctx, engine, d_in, P, H, W, Cin, d_w, d_b, d_r, Cout, k, stride, up, relu, d_o, used_engine,
+                              iters, avg_ms);
     if (s) return s;
     st.back((__half*)out, d_o, n_out);
     return st.finish();
 }
+
+extern "C" {
 
 int hbp_hrnet_set_engine(hbp_ctx* ctx, int engine) { BIND(ctx); return hrnet_set_engine(ctx, engine); }
 

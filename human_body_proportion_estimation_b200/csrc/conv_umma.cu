@@ -54,6 +54,12 @@ struct ConvParams {
     uint32_t row_bytes;          // 64 or 128
     uint32_t tmem_cols;
     uint32_t idesc;
+    // halo mode (3x3 stride 1): the (rs x 10)-pixel halo tile of every Cin chunk is
+    // loaded ONCE and the nine taps are nine descriptor start offsets into it
+    int mode;                    // 0 = one TMA box per tap, 1 = halo tile + shifted descriptors
+    int rs;                      // stacked rows per image in the tile (th + 2)
+    uint32_t a_chunk_bytes;      // smem reserved per Cin chunk (>= box, covers (16*m_tiles+2)*10 rows)
+    uint32_t a_box_bytes;        // bytes one halo box writes
     const float* bias;
     const __half* res;
     __half* out;
@@ -83,8 +89,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     // try_wait suspends in hardware for a bounded time; a pipeline that has not
     // advanced for ~2 s is a bug (wrong expect_tx byte count, bad tensor map):
     // trap instead of hanging the GPU.
-    const long long t0 = clock64();
-    for (;;) {
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
         uint32_t done;
         asm volatile(
             "{\n"
@@ -93,7 +99,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n"
             "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return;
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if ((spins & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();
+        }
     }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -138,11 +148,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // shared-memory matrix descriptor, K-major, hardware swizzle (SM100 format):
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4
 //   [46,48) version=1 | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes) {
+//   base_offset stays 0: tcgen05.mma (like TMA) swizzles on ABSOLUTE shared-memory address
+//   bits, so start addresses and group strides need not be pattern-aligned
+//   (measured: tools/umma_probe.cu, profiles/r01_umma_swizzle_probe.log).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes, uint32_t sbo_bytes = 0) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)((8u * row_bytes) >> 4) << 32;
+    d |= (uint64_t)((sbo_bytes ? sbo_bytes : 8u * row_bytes) >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;
     return d;
@@ -214,21 +227,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
+            // descriptors differ only in their 14-bit start-address field (16-byte units):
+            // build the constant part once, add offsets in the loop (the issuing thread is a
+            // single lane, every instruction it spends is serial latency)
             const int ksteps = p.chunk / 16;
+            const uint64_t d0 = make_desc(0, p.row_bytes);
+            const uint32_t mt_step = (128u * p.row_bytes) >> 4;
+            int s = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < k_iters; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                 mbar_wait(full_bar + 8u * s, ph);
                 tc_fence_after();
-                const uint32_t a_s = a_base + s * p.a_stage_bytes, b_s = b_base + s * p.b_stage_bytes;
+                const uint64_t ad0 = d0 + ((a_base + s * p.a_stage_bytes) >> 4);
+                const uint64_t bd0 = d0 + ((b_base + s * p.b_stage_bytes) >> 4);
                 for (int mt = 0; mt < p.m_tiles; ++mt) {
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint64_t ad = make_desc(a_s + mt * 128u * p.row_bytes + k * 32u, p.row_bytes);
-                        const uint64_t bd = make_desc(b_s + k * 32u, p.row_bytes);
-                        umma_f16(tmem_base + mt * p.n_tile, ad, bd, p.idesc, (it | k) ? 1u : 0u);
+                    const uint64_t ad = ad0 + mt * mt_step;
+                    const uint32_t dt = tmem_base + mt * p.n_tile;
+                    umma_f16(dt, ad, bd0, p.idesc, it ? 1u : 0u);
+                    umma_f16(dt, ad + 2, bd0 + 2, p.idesc, 1u);
+                    if (ksteps == 4) {
+                        umma_f16(dt, ad + 4, bd0 + 4, p.idesc, 1u);
+                        umma_f16(dt, ad + 6, bd0 + 6, p.idesc, 1u);
                     }
                 }
                 umma_commit(empty_bar + 8u * s);          // frees the stage when these MMAs retire
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
             umma_commit(tmem_full_bar);
         }
@@ -297,6 +320,189 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
+
+constexpr int kHaloW = 10;       // 8 output columns + 1 halo column each side
+constexpr int kMaxChunks = 8;
+
+// 3x3 stride-1 convolution, halo mode.  Tile = tn images x th rows x 8 columns.  In shared
+// memory a chunk is the TMA box (chunk channels, 10, rs = th+2, tn): pixel rows of `row_bytes`
+// ordered [n][h][w], i.e. "stacked" image rows q = n*rs + h of 10 pixels each.  MMA row r of
+// M-tile mt is pixel column r%8 of stacked row g = mt*16 + r/8; tap (dy,dx) reads stacked row
+// g+dy, column r%8+dx: a K-major operand with start offset ((mt*16+dy)*10+dx)*row_bytes and an
+// 8-row-group stride of 10 rows.  Stacked rows that are halo rows (g % rs >= th) yield garbage
+// accumulator rows which the epilogue skips.
+__global__ void __launch_bounds__(kThreads)
+conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_base = smem_base;
+    const uint32_t b_base = a_base + p.n_chunks * p.a_chunk_bytes;
+    const uint32_t bar_base = b_base + p.stages * p.b_stage_bytes;
+    const uint32_t a_full = bar_base;                                   // kMaxChunks x 8 B
+    const uint32_t b_full = a_full + 8u * kMaxChunks;
+    const uint32_t b_empty = b_full + 8u * p.stages;
+    const uint32_t tmem_full_bar = b_empty + 8u * p.stages;
+    const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x;
+    const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+    const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+    const int n0 = t * p.tn, h0 = tile_h * p.th, w0 = tile_w * 8;
+    const int n_off = blockIdx.y * p.n_tile;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int c = 0; c < p.n_chunks; ++c) mbar_init(a_full + 8u * c, 1);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(b_full + 8u * s, 1); mbar_init(b_empty + 8u * s, 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int cc = 0; cc < p.n_chunks; ++cc) {
+                mbar_expect_tx(a_full + 8u * cc, p.a_box_bytes);
+                tma_load_4d(a_base + cc * p.a_chunk_bytes, &tmA, a_full + 8u * cc, cc * p.chunk, w0 - 1, h0 - 1, n0);
+            }
+            int it = 0;
+            for (int cc = 0; cc < p.n_chunks; ++cc)
+                for (int tap = 0; tap < 9; ++tap, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(b_empty + 8u * s, ph ^ 1u);
+                    mbar_expect_tx(b_full + 8u * s, (uint32_t)p.n_tile * p.row_bytes);
+                    tma_load_2d(b_base + s * p.b_stage_bytes, &tmB, b_full + 8u * s, cc * p.chunk, tap * p.Cout + n_off);
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const int ksteps = p.chunk / 16;
+            const uint64_t da0 = make_desc(0, p.row_bytes, kHaloW * p.row_bytes);   // A: 8-row groups 10 rows apart
+            const uint64_t db0 = make_desc(0, p.row_bytes);
+            const uint32_t row16 = p.row_bytes >> 4;                                // one pixel row in 16-byte units
+            const uint32_t mt_step = 16u * kHaloW * row16;
+            int s = 0;
+            uint32_t ph = 0, first = 0;
+            for (int cc = 0; cc < p.n_chunks; ++cc) {
+                mbar_wait(a_full + 8u * cc, 0);
+                const uint64_t a_c = da0 + ((a_base + cc * p.a_chunk_bytes) >> 4);
+                for (int dy = 0; dy < 3; ++dy)
+                    for (int dx = 0; dx < 3; ++dx) {
+                        mbar_wait(b_full + 8u * s, ph);
+                        tc_fence_after();
+                        const uint64_t bd0 = db0 + ((b_base + s * p.b_stage_bytes) >> 4);
+                        const uint64_t a_t = a_c + (uint32_t)(dy * kHaloW + dx) * row16;
+                        for (int mt = 0; mt < p.m_tiles; ++mt) {
+                            const uint64_t ad = a_t + mt * mt_step;
+                            const uint32_t dt = tmem_base + mt * p.n_tile;
+                            umma_f16(dt, ad, bd0, p.idesc, first);
+                            umma_f16(dt, ad + 2, bd0 + 2, p.idesc, 1u);
+                            if (ksteps == 4) {
+                                umma_f16(dt, ad + 4, bd0 + 4, p.idesc, 1u);
+                                umma_f16(dt, ad + 6, bd0 + 6, p.idesc, 1u);
+                            }
+                        }
+                        first = 1u;
+                        umma_commit(b_empty + 8u * s);
+                        if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    }
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        const int grp = warp & 3;
+        const int Hout = p.Ho * p.up, Wout = p.Wo * p.up;       // up == 1 for 3x3 convs; kept general
+        // decode this thread's pixels and prefetch nothing yet: wait for the accumulators
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        for (int mt = 0; mt < p.m_tiles; ++mt) {
+            const int r = grp * 32 + lane;
+            const int g = mt * 16 + (r >> 3), col = r & 7;
+            const int nn = g / p.rs, hh = g - nn * p.rs;
+            const int n = n0 + nn, ho = h0 + hh, wo = w0 + col;
+            const bool valid = nn < p.tn && hh < p.th && n < p.P && wo < p.Wo;
+            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                uint32_t rr[16];
+                tmem_ld16(tmem_base + ((uint32_t)(grp * 32) << 16) + (uint32_t)(mt * p.n_tile + c0), rr);
+                tmem_ld_wait();
+                if (!valid) continue;
+                float x[16];
+                const float4* bz = reinterpret_cast<const float4*>(p.bias + n_off + c0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b4 = __ldg(bz + q);
+                    x[4 * q] = __uint_as_float(rr[4 * q]) + b4.x;
+                    x[4 * q + 1] = __uint_as_float(rr[4 * q + 1]) + b4.y;
+                    x[4 * q + 2] = __uint_as_float(rr[4 * q + 2]) + b4.z;
+                    x[4 * q + 3] = __uint_as_float(rr[4 * q + 3]) + b4.w;
+                }
+                const size_t o = ((((size_t)n * Hout + ho) * Wout) + wo) * p.Cout + n_off + c0;
+                if (p.res) {
+                    const uint4 q0 = *reinterpret_cast<const uint4*>(p.res + o);
+                    const uint4 q1 = *reinterpret_cast<const uint4*>(p.res + o + 8);
+                    const __half2* h0p = reinterpret_cast<const __half2*>(&q0);
+                    const __half2* h1p = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 f0 = __half22float2(h0p[q]), f1 = __half22float2(h1p[q]);
+                        x[2 * q] += f0.x; x[2 * q + 1] += f0.y;
+                        x[8 + 2 * q] += f1.x; x[8 + 2 * q + 1] += f1.y;
+                    }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) x[q] = fmaxf(x[q], 0.f);
+                }
+                __align__(16) __half2 pk[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) pk[q] = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+                *reinterpret_cast<uint4*>(p.out + o) = *reinterpret_cast<const uint4*>(&pk[0]);
+                *reinterpret_cast<uint4*>(p.out + o + 8) = *reinterpret_cast<const uint4*>(&pk[4]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// halo tile shape for an Ho x Wo map: tn images x th rows (x 8 columns), m_tiles M-tiles.
+// Returns the fraction of MMA rows that are real output pixels (rows only; columns add Wo/(8*ceil(Wo/8))).
+double pick_halo_tile(int Ho, int* tn, int* th, int* m_tiles) {
+    double best = 0;
+    for (int m = 2; m >= 1; --m)                                // ties go to two M-tiles (weights shared)
+        for (int n = 1; n <= 6; ++n)
+            for (int h = Ho < 16 * m ? Ho : 16 * m; h >= 1; --h) {
+                if (Ho % h) continue;
+                if (n > 1 && h != Ho) continue;                 // stacked images need whole images
+                const int rs = h + 2;
+                // all groups of the tile must be covered: 16m >= n*rs - 2, and the reads stay in the buffer
+                if (16 * m < n * rs - 2) continue;
+                const double frac = (double)(n * h) / (16.0 * m);
+                if (frac > best + 1e-9) { best = frac; *tn = n; *th = h; *m_tiles = m; }
+                break;                                          // largest h for this (m, n)
+            }
+    return best;
+}
+
+int halo_mode_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HBP_CONV_HALO"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
 bool pick_tile(int Ho, int Wo, int m_tiles, int* tn, int* th, int* tw) {
     const int rows = 128 * m_tiles;
     for (int n = 1; n <= 32; n *= 2) {
@@ -343,6 +549,100 @@ bool umma_supported(const HrnetModel& m, const HOp& op) {
 
 void umma_plan_destroy(UmmaPlan* p) { delete p; }
 
+static int encode_weights_map(EncodeTiledFn enc, UmmaPlan* pl, const HrnetModel& m, const HOp& op, int chunk,
+                              int n_tile, CUtensorMapSwizzle sw) {
+    cuuint64_t gdim[2] = {(cuuint64_t)op.cin, (cuuint64_t)op.k * op.k * op.cout};
+    cuuint64_t gstr[1] = {(cuuint64_t)op.cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)chunk, (cuuint32_t)n_tile};
+    cuuint32_t est[2] = {1, 1};
+    CUresult r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, m.d_weights + op.w_off, gdim, gstr, box, est,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        hbp_set_error("cuTensorMapEncodeTiled(B) failed (%d) for %s", (int)r, op.name.c_str());
+        return HBP_ERR_CUDA;
+    }
+    return HBP_OK;
+}
+
+// halo-mode plan (3x3, stride 1).  Returns HBP_OK with *ok = false when the shape does not fit.
+static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaPlan* pl, bool* ok) {
+    *ok = false;
+    const HTensor& ti = m.tensors[op.in];
+    const int Ho = ti.h, Wo = ti.w;
+    ConvParams& p = pl->prm;
+    int tn = 1, th = 0, m_tiles = 1;
+    const double frac = pick_halo_tile(Ho, &tn, &th, &m_tiles);
+    if (frac < 0.5) return HBP_OK;
+    const int chunk = op.cin == 32 ? 32 : 64, n_chunks = op.cin / chunk;
+    if (n_chunks > kMaxChunks) return HBP_OK;
+    const uint32_t row_bytes = chunk * 2;
+    const int tiles_w = (Wo + 7) / 8, tiles_h = Ho / th;
+    int n_tile = 0;
+    for (int c = op.cout < 256 ? op.cout : 256; c >= 16; c -= 16)
+        if (op.cout % c == 0 && m_tiles * c <= 512) { n_tile = c; break; }
+    if (!n_tile) return HBP_OK;
+    // prefer one M-tile when two would leave SMs idle
+    long tiles = (long)((capP + tn - 1) / tn) * tiles_h * tiles_w;
+    if (m_tiles == 2 && tn == 1 && th == 32 && tiles * (op.cout / n_tile) < 2L * ctx->sm_count) { th = 16; m_tiles = 1; }
+    const int tiles_h2 = Ho / th;
+    tiles = (long)((capP + tn - 1) / tn) * tiles_h2 * tiles_w;
+    long ctas = tiles * (op.cout / n_tile);
+    while (ctas < ctx->sm_count && n_tile % 32 == 0 && n_tile > 32) { n_tile /= 2; ctas *= 2; }
+    const int rs = th + 2;
+    const uint32_t a_box_bytes = (uint32_t)(kHaloW * rs * tn) * row_bytes;
+    uint32_t a_chunk_bytes = (uint32_t)((16 * m_tiles + 2) * kHaloW) * row_bytes;
+    if (a_chunk_bytes < a_box_bytes) a_chunk_bytes = a_box_bytes;
+    a_chunk_bytes = (a_chunk_bytes + 1023u) & ~1023u;
+    const uint32_t b_stage = ((uint32_t)n_tile * row_bytes + 1023u) & ~1023u;
+    const uint32_t a_total = a_chunk_bytes * n_chunks;
+    const int k_iters = 9 * n_chunks;
+    int stages = 8;
+    if (stages > k_iters) stages = k_iters;
+    while (stages > 2 && a_total + stages * b_stage > 200 * 1024) --stages;
+    if (a_total + stages * b_stage > 200 * 1024) return HBP_OK;
+    // small CTAs: keep shared memory low enough for >= 3 CTAs per SM
+    while (stages > 4 && a_total + stages * b_stage > 72 * 1024) --stages;
+    if (kHaloW > 256 || rs > 256 || tn > 256) return HBP_OK;
+
+    p.Ho = Ho; p.Wo = Wo; p.Cout = op.cout; p.up = 1; p.relu = op.relu;
+    p.tn = tn; p.th = th; p.tw = 8; p.m_tiles = m_tiles; p.n_tile = n_tile;
+    p.chunk = chunk; p.n_chunks = n_chunks; p.ksz = 3; p.stride = 1;
+    p.tiles_w = tiles_w; p.tiles_h = tiles_h2;
+    p.row_bytes = row_bytes;
+    p.a_stage_bytes = 0; p.b_stage_bytes = b_stage; p.tx_bytes = 0;
+    p.stages = stages;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(m_tiles * n_tile)) cols *= 2;
+    p.tmem_cols = cols;
+    p.idesc = (1u << 4) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    p.mode = 1; p.rs = rs; p.a_chunk_bytes = a_chunk_bytes; p.a_box_bytes = a_box_bytes;
+    p.bias = m.d_bias + op.b_off;
+    p.res = op.res >= 0 ? m.bufs[m.tensors[op.res].buf] : nullptr;
+    p.out = m.bufs[m.tensors[op.out].buf];
+    pl->smem_bytes = (size_t)a_total + (size_t)stages * b_stage + 8 * kMaxChunks + 16 * stages + 32 + 1024;
+    pl->n_splits = op.cout / n_tile;
+
+    EncodeTiledFn enc = get_encode();
+    const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    cuuint64_t gdim[4] = {(cuuint64_t)ti.c, (cuuint64_t)ti.w, (cuuint64_t)ti.h, (cuuint64_t)capP};
+    cuuint64_t gstr[3] = {(cuuint64_t)ti.c * 2, (cuuint64_t)ti.w * ti.c * 2, (cuuint64_t)ti.h * ti.w * ti.c * 2};
+    cuuint32_t box[4] = {(cuuint32_t)chunk, (cuuint32_t)kHaloW, (cuuint32_t)rs, (cuuint32_t)tn};
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, m.bufs[ti.buf], gdim, gstr, box, est,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        hbp_set_error("cuTensorMapEncodeTiled(A halo) failed (%d) for %s box=(%d,%d,%d,%d)", (int)r, op.name.c_str(),
+                      chunk, kHaloW, rs, tn);
+        return HBP_ERR_CUDA;
+    }
+    int st = encode_weights_map(enc, pl, m, op, chunk, n_tile, sw);
+    if (st) return st;
+    *ok = true;
+    return HBP_OK;
+}
+
 int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPlan** out) {
     const HOp& op = m.ops[op_index];
     const HTensor& ti = m.tensors[op.in];
@@ -350,6 +650,20 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     UmmaPlan* pl = new UmmaPlan();
     ConvParams& p = pl->prm;
     memset(&p, 0, sizeof(p));
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { delete pl; hbp_set_error("cuTensorMapEncodeTiled unavailable"); return HBP_ERR_CUDA; }
+    if (!(ctx->attr_flags & ATTR_UMMA)) {
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        ctx->attr_flags |= ATTR_UMMA;
+    }
+    if (op.k == 3 && op.stride == 1 && op.up == 1 && halo_mode_enabled()) {
+        bool ok = false;
+        int st = plan_halo(ctx, m, op, capP, pl, &ok);
+        if (st) { delete pl; return st; }
+        if (ok) { *out = pl; return HBP_OK; }
+        memset(&p, 0, sizeof(p));
+    }
     // N tile: largest divisor of Cout that is a multiple of 16 and <= 256
     int n_tile = 0;
     for (int c = op.cout < 256 ? op.cout : 256; c >= 16; c -= 16)
@@ -399,8 +713,6 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     pl->smem_bytes = (size_t)stages * stage + 16 * stages + 32 + 1024;
     pl->n_splits = op.cout / n_tile;
 
-    EncodeTiledFn enc = get_encode();
-    if (!enc) { delete pl; hbp_set_error("cuTensorMapEncodeTiled unavailable"); return HBP_ERR_CUDA; }
     const CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     {
         cuuint64_t gdim[4] = {(cuuint64_t)ti.c, (cuuint64_t)ti.w, (cuuint64_t)ti.h, (cuuint64_t)capP};
@@ -421,22 +733,8 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
         }
     }
     {
-        cuuint64_t gdim[2] = {(cuuint64_t)op.cin, (cuuint64_t)op.k * op.k * op.cout};
-        cuuint64_t gstr[1] = {(cuuint64_t)op.cin * 2};
-        cuuint32_t box[2] = {(cuuint32_t)p.chunk, (cuuint32_t)n_tile};
-        cuuint32_t est[2] = {1, 1};
-        CUresult r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, m.d_weights + op.w_off, gdim, gstr, box, est,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            delete pl;
-            hbp_set_error("cuTensorMapEncodeTiled(B) failed (%d) for %s", (int)r, op.name.c_str());
-            return HBP_ERR_CUDA;
-        }
-    }
-    if (!(ctx->attr_flags & ATTR_UMMA)) {
-        HBP_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        ctx->attr_flags |= ATTR_UMMA;
+        int st = encode_weights_map(enc, pl, m, op, p.chunk, n_tile, sw);
+        if (st) { delete pl; return st; }
     }
     *out = pl;
     return HBP_OK;
@@ -448,7 +746,8 @@ int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, 
     p.P = P;
     const int tiles_n = (P + p.tn - 1) / p.tn;
     dim3 grid((unsigned)(tiles_n * p.tiles_h * p.tiles_w), (unsigned)pl->n_splits);
-    conv_umma_kernel<<<grid, kThreads, pl->smem_bytes, st>>>(pl->tmA, pl->tmB, p);
+    if (p.mode == 1) conv_umma_halo_kernel<<<grid, kThreads, pl->smem_bytes, st>>>(pl->tmA, pl->tmB, p);
+    else conv_umma_kernel<<<grid, kThreads, pl->smem_bytes, st>>>(pl->tmA, pl->tmB, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return hbp_cuda_fail(e, "conv_umma_kernel", __FILE__, __LINE__);
     return HBP_OK;

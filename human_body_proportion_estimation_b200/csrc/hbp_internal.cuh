@@ -135,4 +135,4 @@ void hrnet_free(hbp_ctx*);
 void hrnet_dims(hbp_ctx*, int* in_h, int* in_w, int* width);
 int hrnet_single_conv(hbp_ctx* ctx, int engine, const __half* in, int P, int H, int W, int Cin,
                       const __half* w, const float* bias, const __half* res, int Cout, int k, int stride,
-                      int up, int relu, __half* out, int* used_engine);
+                      int up, int relu, __half* out, int* used_engine, int iters = 0, float* avg_ms = nullptr);

@@ -624,7 +624,7 @@ int hrnet_debug_tensor(hbp_ctx* ctx, int id, void* out_host, size_t max_bytes, i
 // engine: the unit-test / bring-up entry for the conv kernels.
 int hrnet_single_conv(hbp_ctx* ctx, int engine, const __half* in, int P, int H, int W, int Cin,
                       const __half* w, const float* bias, const __half* res, int Cout, int k, int stride,
-                      int up, int relu, __half* out, int* used_engine) {
+                      int up, int relu, __half* out, int* used_engine, int iters, float* avg_ms) {
     HrnetModel m;
     HTensor ti; ti.c = Cin; ti.h = H; ti.w = W; ti.buf = 0;
     HTensor to; to.c = Cout; to.h = H / stride * up; to.w = W / stride * up; to.buf = 1;
@@ -643,6 +643,16 @@ int hrnet_single_conv(hbp_ctx* ctx, int engine, const __half* in, int P, int H, 
         status = umma_plan_create(ctx, m, 0, P, &plan);
         if (status == HBP_OK) {
             status = umma_launch(ctx, m, 0, plan, P, ctx->stream);
+            if (iters > 0 && avg_ms && status == HBP_OK) {      // timing loop (bring-up / microbenchmark)
+                umma_launch(ctx, m, 0, plan, P, ctx->stream);
+                cudaEventRecord(ctx->ev_start[7], ctx->stream);
+                for (int i = 0; i < iters && status == HBP_OK; ++i) status = umma_launch(ctx, m, 0, plan, P, ctx->stream);
+                cudaEventRecord(ctx->ev_stop[7], ctx->stream);
+                cudaEventSynchronize(ctx->ev_stop[7]);
+                cudaEventElapsedTime(avg_ms, ctx->ev_start[7], ctx->ev_stop[7]);
+                *avg_ms /= iters;
+                ctx->launches += iters + 1;
+            }
             // the tensor maps are kernel parameters (copied at launch): the plan can go
             umma_plan_destroy(plan);
         }
@@ -653,6 +663,17 @@ int hrnet_single_conv(hbp_ctx* ctx, int engine, const __half* in, int P, int H, 
         dim3 grid((unsigned)((total + kTP - 1) / kTP), (Cout + kTC - 1) / kTC);
         conv_simt_kernel<<<grid, 256, 0, ctx->stream>>>(in, w, bias, res, out, P, H, W, Cin, Ho, Wo, Cout, k,
                                                         stride, up, relu);
+        if (iters > 0 && avg_ms) {
+            cudaEventRecord(ctx->ev_start[7], ctx->stream);
+            for (int i = 0; i < iters; ++i)
+                conv_simt_kernel<<<grid, 256, 0, ctx->stream>>>(in, w, bias, res, out, P, H, W, Cin, Ho, Wo, Cout, k,
+                                                                stride, up, relu);
+            cudaEventRecord(ctx->ev_stop[7], ctx->stream);
+            cudaEventSynchronize(ctx->ev_stop[7]);
+            cudaEventElapsedTime(avg_ms, ctx->ev_start[7], ctx->ev_stop[7]);
+            *avg_ms /= iters;
+            ctx->launches += iters;
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) status = hbp_cuda_fail(e, "conv_simt_kernel", __FILE__, __LINE__);
         if (used_engine) *used_engine = 0;

@@ -190,8 +190,9 @@ class Engine:
         self.hrnet = (width, in_h, in_w)
         return weights
 
-    def conv2d_nhwc(self, x, w, bias, residual=None, stride=1, up=1, relu=False, engine=1):
-        """x (P,H,W,Cin) f16, w (Cout,Cin,k,k) -> (P,H/stride*up,W/stride*up,Cout) f16, used_engine"""
+    def conv2d_nhwc(self, x, w, bias, residual=None, stride=1, up=1, relu=False, engine=1, time_iters=0):
+        """x (P,H,W,Cin) f16, w (Cout,Cin,k,k) -> (P,H/stride*up,W/stride*up,Cout) f16, used_engine
+        (+ average device ms per launch when time_iters > 0)"""
         x = _c(x, np.float16)
         P, H, W, Cin = x.shape
         Cout, _, k, _ = w.shape
@@ -200,6 +201,12 @@ class Engine:
         out = np.empty((P, H // stride * up, W // stride * up, Cout), np.float16)
         r = _c(residual, np.float16) if residual is not None else None
         used = C.c_int(-1)
+        if time_iters > 0:
+            ms = C.c_float()
+            check(self._lib.hbp_conv2d_nhwc_timed(self._ctx, int(engine), ptr(x), P, H, W, Cin, ptr(wb), ptr(b), ptr(r),
+                                                  Cout, k, stride, up, int(relu), ptr(out), C.byref(used), HOST,
+                                                  int(time_iters), C.byref(ms)))
+            return out, used.value, ms.value
         check(self._lib.hbp_conv2d_nhwc(self._ctx, int(engine), ptr(x), P, H, W, Cin, ptr(wb), ptr(b), ptr(r),
                                         Cout, k, stride, up, int(relu), ptr(out), C.byref(used), HOST))
         return out, used.value

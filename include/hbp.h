@@ -186,6 +186,12 @@ HBP_API int hbp_conv2d_nhwc(hbp_ctx* ctx, int engine, const void* in_f16, int P,
                             const void* weights_f16, const float* bias, const void* residual_f16,
                             int Cout, int k, int stride, int up, int relu, void* out_f16,
                             int* used_engine, int mem);
+/* Same operator, launched `iters` more times back to back between two CUDA events on the
+ * context's stream: *avg_ms = device time per launch (the kernel-level roofline probe). */
+HBP_API int hbp_conv2d_nhwc_timed(hbp_ctx* ctx, int engine, const void* in_f16, int P, int H, int W, int Cin,
+                                  const void* weights_f16, const float* bias, const void* residual_f16,
+                                  int Cout, int k, int stride, int up, int relu, void* out_f16,
+                                  int* used_engine, int mem, int iters, float* avg_ms);
 /* which conv engine the loaded model runs: 0 = SIMT direct conv,
  * 1 = tcgen05/TMEM implicit GEMM fed by TMA. */
 HBP_API int hbp_hrnet_set_engine(hbp_ctx* ctx, int engine);

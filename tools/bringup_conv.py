@@ -33,6 +33,11 @@ CASES = [
     (2, 64, 48, 256, 64, 3, 2, 1, False, True),     # transition1.1
     (2, 16, 12, 128, 256, 3, 2, 1, True, False),    # fuse down to branch 3
     (64, 64, 48, 32, 32, 3, 1, 1, True, True),      # full batch
+    (3, 24, 18, 192, 192, 3, 1, 1, True, True),     # W48 branch 2 (halo rows 24 -> 75 % tiles)
+    (5, 12, 9, 384, 384, 3, 1, 1, True, False),     # W48 branch 3 (stacked images, ragged width)
+    (64, 32, 24, 64, 64, 3, 1, 1, True, True),      # full batch branch 1
+    (64, 16, 12, 128, 128, 3, 1, 1, True, True),    # full batch branch 2
+    (64, 8, 6, 256, 256, 3, 1, 1, True, True),      # full batch branch 3
 ]
 
 
