@@ -148,6 +148,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+// One lane of a converged warp.  tcgen05.mma / TMA / commit take their operands from the
+// warp-uniform register file: the role loops below therefore run warp-wide on provably
+// uniform values (kernel parameters, loop counters, shuffled warp index) and only the issue
+// itself sits under elect.sync -- inside a divergent `if (lane == 0)` the compiler has to wrap
+// every such instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~200 cycles
+// per MMA, measured: profiles/r01_conv_phase_trace.log).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major, hardware swizzle (SM100 format):
@@ -181,8 +199,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t empty_bar = bar_base + 8u * p.stages;
     const uint32_t tmem_full_bar = bar_base + 16u * p.stages;
     const uint32_t tmem_slot = tmem_full_bar + 8u;
+    float* s_bias = reinterpret_cast<float*>(smem_raw + (tmem_slot + 8u - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int taps = p.ksz * p.ksz;
     const int k_iters = taps * p.n_chunks;
 
@@ -204,34 +223,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+    for (int i = threadIdx.x; i < p.n_tile; i += kThreads) s_bias[i] = p.bias[blockIdx.y * p.n_tile + i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            const int pad = p.ksz / 2;
-            int it = 0;
-            for (int tap = 0; tap < taps; ++tap) {
-                const int dy = tap / p.ksz - pad, dx = tap % p.ksz - pad;
-                for (int cc = 0; cc < p.n_chunks; ++cc, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                    mbar_wait(empty_bar + 8u * s, ph ^ 1u);
+        // ===== TMA producer (warp-wide control flow, one elected lane issues) =====
+        const int pad = p.ksz / 2;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tap = 0; tap < taps; ++tap) {
+            const int dy = tap / p.ksz - pad, dx = tap % p.ksz - pad;
+            for (int cc = 0; cc < p.n_chunks; ++cc) {
+                mbar_wait(empty_bar + 8u * s, ph ^ 1u);
+                if (elect_one()) {
                     mbar_expect_tx(full_bar + 8u * s, p.tx_bytes);
                     tma_load_4d(a_base + s * p.a_stage_bytes, &tmA, full_bar + 8u * s,
                                 cc * p.chunk, w0 * p.stride + dx, h0 * p.stride + dy, n0);
                     tma_load_2d(b_base + s * p.b_stage_bytes, &tmB, full_bar + 8u * s,
                                 cc * p.chunk, tap * p.Cout + n_off);
                 }
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (warp-wide control flow, one elected lane issues) =====
+        {
             // descriptors differ only in their 14-bit start-address field (16-byte units):
             // build the constant part once, add offsets in the loop (the issuing thread is a
             // single lane, every instruction it spends is serial latency)
@@ -245,75 +267,96 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc_fence_after();
                 const uint64_t ad0 = d0 + ((a_base + s * p.a_stage_bytes) >> 4);
                 const uint64_t bd0 = d0 + ((b_base + s * p.b_stage_bytes) >> 4);
-                for (int mt = 0; mt < p.m_tiles; ++mt) {
-                    const uint64_t ad = ad0 + mt * mt_step;
-                    const uint32_t dt = tmem_base + mt * p.n_tile;
-                    umma_f16(dt, ad, bd0, p.idesc, it ? 1u : 0u);
-                    umma_f16(dt, ad + 2, bd0 + 2, p.idesc, 1u);
-                    if (ksteps == 4) {
-                        umma_f16(dt, ad + 4, bd0 + 4, p.idesc, 1u);
-                        umma_f16(dt, ad + 6, bd0 + 6, p.idesc, 1u);
+                if (elect_one()) {
+                    for (int mt = 0; mt < p.m_tiles; ++mt) {
+                        const uint64_t ad = ad0 + mt * mt_step;
+                        const uint32_t dt = tmem_base + mt * p.n_tile;
+                        umma_f16(dt, ad, bd0, p.idesc, it ? 1u : 0u);
+                        umma_f16(dt, ad + 2, bd0 + 2, p.idesc, 1u);
+                        if (ksteps == 4) {
+                            umma_f16(dt, ad + 4, bd0 + 4, p.idesc, 1u);
+                            umma_f16(dt, ad + 6, bd0 + 6, p.idesc, 1u);
+                        }
                     }
+                    umma_commit(empty_bar + 8u * s);      // frees the stage when these MMAs retire
                 }
-                umma_commit(empty_bar + 8u * s);          // frees the stage when these MMAs retire
+                __syncwarp();
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
-            umma_commit(tmem_full_bar);
+            if (elect_one()) umma_commit(tmem_full_bar);
+            __syncwarp();
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global =====
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
+        // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> global =====
         const int grp = warp & 3;                          // TMEM lane group this warp may read
         const int Hout = p.Ho * p.up, Wout = p.Wo * p.up;
-        for (int mt = 0; mt < p.m_tiles; ++mt) {
+        bool valid[2];
+        int pn[2], ph_[2], pw[2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
             const int R = mt * 128 + grp * 32 + lane;
-            const int ww = R % p.tw, hh = (R / p.tw) % p.th, nn = R / (p.tw * p.th);
-            const int n = n0 + nn, ho = h0 + hh, wo = w0 + ww;
-            const bool valid = n < p.P;
-            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(tmem_base + ((uint32_t)(grp * 32) << 16) + (uint32_t)(mt * p.n_tile + c0), r);
-                tmem_ld_wait();
-                if (!valid) continue;
-                float v[16];
-                const float4* bz = reinterpret_cast<const float4*>(p.bias + n_off + c0);
+            pw[mt] = w0 + R % p.tw; ph_[mt] = h0 + (R / p.tw) % p.th; pn[mt] = n0 + R / (p.tw * p.th);
+            valid[mt] = mt < p.m_tiles && pn[mt] < p.P;
+        }
+        // residual of the first 64 columns of the first M-tile is in flight before the accumulator is ready
+        const bool direct = p.up == 1;
+        uint4 rq[8];
+        auto fetch_res = [&](int mt, int cg) {
+            const size_t o = ((((size_t)pn[mt] * Hout + ph_[mt]) * Wout) + pw[mt]) * p.Cout + n_off + cg;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 b4 = __ldg(bz + q);
-                    v[4 * q] = __uint_as_float(r[4 * q]) + b4.x;
-                    v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
-                    v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
-                    v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
-                }
-                for (int uy = 0; uy < p.up; ++uy)
-                    for (int ux = 0; ux < p.up; ++ux) {
-                        const size_t o = ((((size_t)n * Hout + ho * p.up + uy) * Wout) + wo * p.up + ux) * p.Cout + n_off + c0;
-                        float x[16];
+            for (int q = 0; q < 8; ++q)
+                if (cg + q * 8 < p.n_tile) rq[q] = *reinterpret_cast<const uint4*>(p.res + o + q * 8);
+        };
+        if (direct && p.res && valid[0]) fetch_res(0, 0);
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        for (int mt = 0; mt < p.m_tiles; ++mt) {
+            for (int cg = 0; cg < p.n_tile; cg += 64) {
+                if (direct && p.res && valid[mt] && (mt | cg)) fetch_res(mt, cg);
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) x[q] = v[q];
-                        if (p.res) {
-                            const uint4 q0 = *reinterpret_cast<const uint4*>(p.res + o);
-                            const uint4 q1 = *reinterpret_cast<const uint4*>(p.res + o + 8);
-                            const __half2* h0p = reinterpret_cast<const __half2*>(&q0);
-                            const __half2* h1p = reinterpret_cast<const __half2*>(&q1);
+                for (int cq = 0; cq < 4; ++cq) {
+                    const int c0 = cg + cq * 16;
+                    if (c0 >= p.n_tile) break;
+                    uint32_t r[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(grp * 32) << 16) + (uint32_t)(mt * p.n_tile + c0), r);
+                    tmem_ld_wait();
+                    if (!valid[mt]) continue;
+                    float v[16];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float2 f0 = __half22float2(h0p[q]), f1 = __half22float2(h1p[q]);
-                                x[2 * q] += f0.x; x[2 * q + 1] += f0.y;
-                                x[8 + 2 * q] += f1.x; x[8 + 2 * q + 1] += f1.y;
+                    for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]) + s_bias[c0 + q];
+                    for (int uy = 0; uy < p.up; ++uy)
+                        for (int ux = 0; ux < p.up; ++ux) {
+                            const size_t o = ((((size_t)pn[mt] * Hout + ph_[mt] * p.up + uy) * Wout) + pw[mt] * p.up + ux) * p.Cout + n_off + c0;
+                            float x[16];
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) x[q] = v[q];
+                            if (p.res) {
+                                uint4 q0, q1;
+                                if (direct) { q0 = rq[2 * cq]; q1 = rq[2 * cq + 1]; }
+                                else {
+                                    q0 = *reinterpret_cast<const uint4*>(p.res + o);
+                                    q1 = *reinterpret_cast<const uint4*>(p.res + o + 8);
+                                }
+                                const __half2* h0p = reinterpret_cast<const __half2*>(&q0);
+                                const __half2* h1p = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 f0 = __half22float2(h0p[q]), f1 = __half22float2(h1p[q]);
+                                    x[2 * q] += f0.x; x[2 * q + 1] += f0.y;
+                                    x[8 + 2 * q] += f1.x; x[8 + 2 * q + 1] += f1.y;
+                                }
                             }
-                        }
-                        if (p.relu) {
+                            if (p.relu) {
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) x[q] = fmaxf(x[q], 0.f);
-                        }
-                        __align__(16) __half2 pk[8];
+                                for (int q = 0; q < 16; ++q) x[q] = fmaxf(x[q], 0.f);
+                            }
+                            __align__(16) __half2 pk[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) pk[q] = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
-                        *reinterpret_cast<uint4*>(p.out + o) = *reinterpret_cast<const uint4*>(&pk[0]);
-                        *reinterpret_cast<uint4*>(p.out + o + 8) = *reinterpret_cast<const uint4*>(&pk[4]);
-                    }
+                            for (int q = 0; q < 8; ++q) pk[q] = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+                            *reinterpret_cast<uint4*>(p.out + o) = *reinterpret_cast<const uint4*>(&pk[0]);
+                            *reinterpret_cast<uint4*>(p.out + o + 8) = *reinterpret_cast<const uint4*>(&pk[4]);
+                        }
+                }
             }
         }
         tc_fence_before();
@@ -360,10 +403,10 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t tmem_slot = acc_empty + 16u;
     float* s_bias = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int n_off = blockIdx.y * p.n_tile;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
-    long long* dbg = (p.dbg && blockIdx.x < 64 && blockIdx.y == 0) ? p.dbg + blockIdx.x * 8 : nullptr;
+    long long* dbg = (p.dbg && blockIdx.x < 64 && blockIdx.y == 0) ? p.dbg + blockIdx.x * 32 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
     if (warp == 0 && lane == 0) {
@@ -381,35 +424,40 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
     const uint32_t acc_stride = (uint32_t)(p.m_tiles * p.n_tile);      // TMEM columns per accumulator buffer
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            int it = 0, j = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
-                const int tile_w = tile % p.tiles_w, tile_h = (tile / p.tiles_w) % p.tiles_h;
-                const int n0 = (tile / tiles_per_img) * p.tn, h0 = tile_h * p.th, w0 = tile_w * 8;
-                // the halo buffers are free once the previous tile's MMAs have retired
-                if (j > 0) mbar_wait(acc_full + 8u * ((j - 1) % p.acc_bufs), (uint32_t)(((j - 1) / p.acc_bufs) & 1));
+        // ===== TMA producer (warp-wide control flow, one elected lane issues) =====
+        int s = 0, j = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
+            const int tile_w = tile % p.tiles_w, tile_h = (tile / p.tiles_w) % p.tiles_h;
+            const int n0 = (tile / tiles_per_img) * p.tn, h0 = tile_h * p.th, w0 = tile_w * 8;
+            // the halo buffers are free once the previous tile's MMAs have retired
+            if (j > 0) mbar_wait(acc_full + 8u * ((j - 1) % p.acc_bufs), (uint32_t)(((j - 1) / p.acc_bufs) & 1));
+            if (elect_one()) {
                 for (int cc = 0; cc < p.n_chunks; ++cc) {
                     mbar_expect_tx(a_full + 8u * cc, p.a_box_bytes);
                     tma_load_4d(a_base + cc * p.a_chunk_bytes, &tmA, a_full + 8u * cc, cc * p.chunk, w0 - 1, h0 - 1, n0);
                 }
-                for (int cc = 0; cc < p.n_chunks; ++cc)
-                    for (int tap = 0; tap < 9; ++tap, ++it) {
-                        const int s = it % p.stages;
-                        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                        mbar_wait(b_empty + 8u * s, ph ^ 1u);
+            }
+            __syncwarp();
+            for (int cc = 0; cc < p.n_chunks; ++cc)
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(b_empty + 8u * s, ph ^ 1u);
+                    if (elect_one()) {
                         mbar_expect_tx(b_full + 8u * s, (uint32_t)p.n_tile * p.row_bytes);
                         tma_load_2d(b_base + s * p.b_stage_bytes, &tmB, b_full + 8u * s, cc * p.chunk, tap * p.Cout + n_off);
                     }
-            }
+                    __syncwarp();
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (warp-wide control flow, one elected lane issues) =====
+        {
             const int ksteps = p.chunk / 16;
             const uint64_t da0 = make_desc(0, p.row_bytes, kHaloW * p.row_bytes);   // A: 8-row groups 10 rows apart
             const uint64_t db0 = make_desc(0, p.row_bytes);
@@ -428,32 +476,38 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 uint32_t first = 0;
                 for (int cc = 0; cc < p.n_chunks; ++cc) {
                     mbar_wait(a_full + 8u * cc, (uint32_t)(j & 1));
-                    if (dbg && cc == 0 && j == 0) dbg[2] = clock64();
+                    if (dbg && cc == 0 && j == 0 && lane == 0) dbg[2] = clock64();
                     const uint64_t a_c = da0 + ((a_base + cc * p.a_chunk_bytes) >> 4);
                     for (int dy = 0; dy < 3; ++dy)
                         for (int dx = 0; dx < 3; ++dx) {
                             mbar_wait(b_full + 8u * s, ph);
-                            if (dbg && !first && j == 0) dbg[3] = clock64();
+                            if (dbg && !first && j == 0 && lane == 0) dbg[3] = clock64();
+                            if (dbg && j == 0 && cc == 0 && lane == 0) dbg[8 + dy * 3 + dx] = clock64();
                             tc_fence_after();
                             const uint64_t bd0 = db0 + ((b_base + s * p.b_stage_bytes) >> 4);
                             const uint64_t a_t = a_c + (uint32_t)(dy * kHaloW + dx) * row16;
-                            for (int mt = 0; mt < p.m_tiles; ++mt) {
-                                const uint64_t ad = a_t + mt * mt_step;
-                                const uint32_t dt = d_base + mt * p.n_tile;
-                                umma_f16(dt, ad, bd0, p.idesc, first);
-                                umma_f16(dt, ad + 2, bd0 + 2, p.idesc, 1u);
-                                if (ksteps == 4) {
-                                    umma_f16(dt, ad + 4, bd0 + 4, p.idesc, 1u);
-                                    umma_f16(dt, ad + 6, bd0 + 6, p.idesc, 1u);
+                            if (elect_one()) {
+                                for (int mt = 0; mt < p.m_tiles; ++mt) {
+                                    const uint64_t ad = a_t + mt * mt_step;
+                                    const uint32_t dt = d_base + mt * p.n_tile;
+                                    umma_f16(dt, ad, bd0, p.idesc, first);
+                                    umma_f16(dt, ad + 2, bd0 + 2, p.idesc, 1u);
+                                    if (ksteps == 4) {
+                                        umma_f16(dt, ad + 4, bd0 + 4, p.idesc, 1u);
+                                        umma_f16(dt, ad + 6, bd0 + 6, p.idesc, 1u);
+                                    }
                                 }
+                                umma_commit(b_empty + 8u * s);
                             }
+                            __syncwarp();
                             first = 1u;
-                            umma_commit(b_empty + 8u * s);
+                            if (dbg && j == 0 && cc == 0 && lane == 0) dbg[20 + dy * 3 + dx] = clock64();
                             if (++s == p.stages) { s = 0; ph ^= 1u; }
                         }
                 }
-                umma_commit(acc_full + 8u * ab);
-                if (dbg && j == 0) dbg[4] = clock64();
+                if (elect_one()) umma_commit(acc_full + 8u * ab);
+                __syncwarp();
+                if (dbg && j == 0 && lane == 0) dbg[4] = clock64();
             }
         }
     } else {
@@ -654,6 +708,13 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     // prefer one M-tile when two would leave SMs idle
     long tiles = (long)((capP + tn - 1) / tn) * tiles_h * tiles_w;
     if (m_tiles == 2 && tn == 1 && th == 32 && tiles * (op.cout / n_tile) < 2L * ctx->sm_count) { th = 16; m_tiles = 1; }
+    // tiles are scarce (low-resolution branches at small batch): latency per CTA matters more than
+    // the share of useful MMA rows -- take the smallest tile (one image, one M-tile)
+    if (tiles * (op.cout / n_tile) < ctx->sm_count && (tn > 1 || m_tiles > 1)) {
+        tn = 1; m_tiles = 1;
+        th = Ho < 16 ? Ho : 16;
+        while (Ho % th) --th;
+    }
     const int tiles_h2 = Ho / th;
     tiles = (long)((capP + tn - 1) / tn) * tiles_h2 * tiles_w;
     long ctas = tiles * (op.cout / n_tile);
@@ -693,11 +754,23 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     pl->smem_bytes = (size_t)a_total + (size_t)stages * b_stage + 8 * kMaxChunks + 16 * stages + 64 + (size_t)n_tile * 4 + 1024;
     pl->n_splits = op.cout / n_tile;
     {
-        int occ = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_umma_halo_kernel, kThreads, pl->smem_bytes);
+        // resident CTAs per SM: registers, shared memory (+1 KB the runtime reserves per CTA),
+        // threads and TMEM columns
+        cudaFuncAttributes fa;
+        int regs = 80;
+        if (cudaFuncGetAttributes(&fa, conv_umma_halo_kernel) == cudaSuccess && fa.numRegs > 0) regs = fa.numRegs;
+        const int regs_per_cta = ((regs + 7) / 8 * 8) * kThreads;
+        int occ = 65536 / regs_per_cta;
+        const int by_smem = (int)((227 * 1024) / (pl->smem_bytes + 1024));
+        const int by_threads = 2048 / kThreads;
         const int by_tmem = 512 / (int)cols;
+        if (occ > by_smem) occ = by_smem;
+        if (occ > by_threads) occ = by_threads;
         if (occ > by_tmem) occ = by_tmem;
         pl->occ = occ < 1 ? 1 : occ;
+        if (getenv("HBP_CONV_TRACE"))
+            fprintf(stderr, "[plan] %s halo tile tn=%d th=%d m=%d n_tile=%d stages=%d acc_bufs=%d tmem=%u regs=%d smem=%zu occ=%d\n",
+                    op.name.c_str(), tn, th, m_tiles, n_tile, stages, p.acc_bufs, cols, regs, pl->smem_bytes, pl->occ);
     }
 
     EncodeTiledFn enc = get_encode();
@@ -790,7 +863,7 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     p.bias = m.d_bias + op.b_off;
     p.res = op.res >= 0 ? m.bufs[m.tensors[op.res].buf] : nullptr;
     p.out = m.bufs[m.tensors[op.out].buf];
-    pl->smem_bytes = (size_t)stages * stage + 16 * stages + 32 + 1024;
+    pl->smem_bytes = (size_t)stages * stage + 16 * stages + 64 + (size_t)n_tile * 4 + 1024;
     pl->n_splits = op.cout / n_tile;
 
     const CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -842,17 +915,20 @@ int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, 
         static int traced = 0;
         if (traced++ % 8 == 3) {        // a warm launch of every shape the process runs
             long long* d = nullptr;
-            cudaMalloc(&d, 64 * 8 * sizeof(long long));
-            cudaMemset(d, 0, 64 * 8 * sizeof(long long));
+            cudaMalloc(&d, 64 * 32 * sizeof(long long));
+            cudaMemset(d, 0, 64 * 32 * sizeof(long long));
             p.dbg = d;
             conv_umma_halo_kernel<<<grid, kThreads, pl->smem_bytes, st>>>(pl->tmA, pl->tmB, p);
             cudaStreamSynchronize(st);
-            long long h[64 * 8];
+            static long long h[64 * 32];
             cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
             cudaFree(d);
             const int n = grid.x < 64 ? (int)grid.x : 64;
-            double acc[8] = {0};
-            for (int i = 0; i < n; ++i) for (int k = 1; k < 8; ++k) acc[k] += (double)(h[i * 8 + k] - h[i * 8]);
+            double acc[32] = {0};
+            for (int i = 0; i < n; ++i) for (int k = 1; k < 32; ++k) acc[k] += (double)(h[i * 32 + k] - h[i * 32]);
+            fprintf(stderr, "[taps] B landed / MMAs issued per tap (cycles from CTA start):");
+            for (int k = 0; k < 9; ++k) fprintf(stderr, " %.0f/%.0f", acc[8 + k] / n, acc[20 + k] / n);
+            fprintf(stderr, "\n");
             fprintf(stderr, "[trace] grid=(%u,%u) smem=%zu stages=%d m=%d n_tile=%d chunks=%d | cycles from CTA start: setup %.0f, A0 landed %.0f, "
                     "B0 landed %.0f, MMAs issued %.0f, accum ready %.0f, epilogue done %.0f, dealloc %.0f\n", grid.x, grid.y, pl->smem_bytes,
                     p.stages, p.m_tiles, p.n_tile, p.n_chunks, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n, acc[6] / n, acc[7] / n);
