@@ -124,7 +124,11 @@ void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const
             x[i] = y;
         }
     }
-    // fuse: y_i = relu( sum_j f_ij(x_j) ), f_ii = identity
+    // fuse: y_i = relu( sum_j f_ij(x_j) ), f_ii = identity.  Terms from higher-resolution
+    // branches (j < i) are stride-2 conv chains whose last conv accumulates into y_i; terms
+    // from lower-resolution branches (j > i) are 1x1 convs at LOW resolution followed by ONE
+    // coalesced upsample-add over all of them (a scatter inside the conv epilogue serialises
+    // up*up dependent load/store pairs per thread).
     B.join();
     const int n_out = multi_scale_output ? nb : 1;
     std::vector<int> y(n_out);
@@ -133,28 +137,41 @@ void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const
         const HTensor ti = m.tensors[x[i]];
         y[i] = B.new_tensor(ti.c, ti.h, ti.w);
         int res = x[i];                    // first term adds the identity branch
-        int remaining = nb - 1;
-        for (int j = 0; j < nb; ++j) {
-            if (j == i) continue;
-            --remaining;
-            const int last = remaining == 0;
-            if (j > i) {
-                B.conv(pre + S(".fuse_layers.%d.%d.0", i, j), x[j], ch[i], 1, 1, last, res, y[i], 1 << (j - i));
-            } else {
-                int cur = x[j];
-                for (int k = 0; k < i - j; ++k) {
-                    const std::string nm = pre + S(".fuse_layers.%d.%d.%d.0", i, j, k);
-                    if (k == i - j - 1) {
-                        B.conv(nm, cur, ch[i], 3, 2, last, res, y[i]);
-                        if (cur != x[j]) B.release(cur, true);
-                    } else {
-                        const int nxt = B.conv(nm, cur, ch[j], 3, 2, 1);
-                        if (cur != x[j]) B.release(cur, true);
-                        cur = nxt;
-                    }
+        for (int j = 0; j < i; ++j) {
+            const int last = (i == nb - 1) && (j == i - 1);
+            int cur = x[j];
+            for (int k = 0; k < i - j; ++k) {
+                const std::string nm = pre + S(".fuse_layers.%d.%d.%d.0", i, j, k);
+                if (k == i - j - 1) {
+                    B.conv(nm, cur, ch[i], 3, 2, last, res, y[i]);
+                    if (cur != x[j]) B.release(cur, true);
+                } else {
+                    const int nxt = B.conv(nm, cur, ch[j], 3, 2, 1);
+                    if (cur != x[j]) B.release(cur, true);
+                    cur = nxt;
                 }
             }
             res = y[i];
+        }
+        if (i < nb - 1) {
+            int lows[3] = {-1, -1, -1}, ups[3] = {1, 1, 1}, nl = 0;
+            for (int j = i + 1; j < nb; ++j) {
+                lows[nl] = B.conv(pre + S(".fuse_layers.%d.%d.0", i, j), x[j], ch[i], 1, 1, 0);
+                ups[nl++] = 1 << (j - i);
+            }
+            HOp op;
+            op.kind = OP_UPADD;
+            op.name = pre + S(".fuse_layers.%d.upadd", i);
+            op.in = lows[0]; op.in2 = lows[1]; op.in3 = lows[2];
+            op.up = ups[0]; op.up2 = ups[1]; op.up3 = ups[2];
+            op.res = res; op.out = y[i];
+            op.cin = op.cout = ch[i];
+            op.relu = 1;
+            op.stream = B.cur_stream;
+            op.join_before = B.pending_join ? 1 : 0;
+            B.pending_join = false;
+            m.ops.push_back(op);
+            for (int q = 0; q < nl; ++q) B.release(lows[q], true);
         }
     }
     for (int j = 0; j < nb; ++j) B.release(x[j], false);
@@ -310,6 +327,44 @@ head_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const f
         if constexpr (sizeof(OutT) == 2) *o = __float2half_rn(acc[j]);
         else *o = acc[j];
     }
+}
+
+// out = act(res + up(a) [+ up2(b)] [+ up3(c)]), NHWC fp16, nearest upsample; 16 bytes per thread
+__global__ void __launch_bounds__(256)
+upsample_add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, const __half* __restrict__ c,
+                    const __half* res, __half* out, int P, int H, int W, int C, int fa, int fb, int fc, int relu) {
+    const int c8n = C >> 3;
+    const size_t total = (size_t)P * H * W * c8n;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c8 = (int)(i % c8n);
+    const size_t pix = i / c8n;
+    const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
+    float acc[8];
+    {
+        const uint4 q = *reinterpret_cast<const uint4*>(res + pix * C + c8 * 8);
+        const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hq[k]); acc[2 * k] = f.x; acc[2 * k + 1] = f.y; }
+    }
+    auto add = [&](const __half* src, int f) {
+        const int hs = H / f, ws = W / f;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)n * hs + h / f) * ws + w / f) * C + c8 * 8));
+        const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 t = __half22float2(hq[k]); acc[2 * k] += t.x; acc[2 * k + 1] += t.y; }
+    };
+    add(a, fa);
+    if (b) add(b, fb);
+    if (c) add(c, fc);
+    __align__(16) __half2 pk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float x0 = acc[2 * k], x1 = acc[2 * k + 1];
+        if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+        pk[k] = __floats2half2_rn(x0, x1);
+    }
+    *reinterpret_cast<uint4*>(out + pix * C + c8 * 8) = *reinterpret_cast<const uint4*>(pk);
 }
 
 // Generic fused conv, NHWC fp16, weights [tap][cout][cin], fp32 accumulate.
@@ -526,6 +581,13 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
             else
                 head_kernel<float><<<(unsigned)((total + 127) / 128), 128, sm, st>>>(
                     m->bufs[ti.buf], m->d_weights + op.w_off, m->d_bias + op.b_off, (float*)heatmaps, P, ti.h * ti.w, ti.c);
+        } else if (op.kind == OP_UPADD) {
+            const HTensor& to = m->tensors[op.out];
+            const size_t total = (size_t)P * to.h * to.w * (to.c / 8);
+            upsample_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+                m->bufs[m->tensors[op.in].buf], op.in2 >= 0 ? m->bufs[m->tensors[op.in2].buf] : nullptr,
+                op.in3 >= 0 ? m->bufs[m->tensors[op.in3].buf] : nullptr, m->bufs[m->tensors[op.res].buf],
+                m->bufs[to.buf], P, to.h, to.w, to.c, op.up, op.up2, op.up3, op.relu);
         } else {
             bool done = false;
             if (m->engine == 1 && umma_supported(*m, op)) {
@@ -711,6 +773,7 @@ extern "C" int hbp_hrnet_describe(int width, int in_h, int in_w, char* buf, size
     std::string s;
     char line[256];
     for (const HOp& op : m.ops) {
+        if (op.kind == OP_UPADD) continue;            // no parameters
         int ho = 0, wo = 0;
         if (op.kind == OP_STEM1) { ho = m.in_h / 2; wo = m.in_w / 2; }
         else { ho = m.tensors[op.in].h / op.stride; wo = m.tensors[op.in].w / op.stride; }

@@ -12,7 +12,7 @@ struct HTensor {
     int buf = -1;               // index into the per-batch buffer table
 };
 
-enum HOpKind { OP_STEM1 = 0, OP_CONV = 1, OP_HEAD = 2 };
+enum HOpKind { OP_STEM1 = 0, OP_CONV = 1, OP_HEAD = 2, OP_UPADD = 3 };
 
 // out = act( conv_k,s(in) + bias [+ residual] ), optionally replicated `up` x `up`
 // (nearest upsample fused into the store; residual is read at the upsampled position)
@@ -20,6 +20,7 @@ struct HOp {
     int kind = OP_CONV;
     std::string name;           // public HRNet state_dict prefix, e.g. "stage2.0.branches.1.0.conv1"
     int in = -1, out = -1, res = -1;   // tensor ids (res = -1: none; may equal out: in-place accumulate)
+    int in2 = -1, in3 = -1, up2 = 1, up3 = 1;   // OP_UPADD: out = act(res + up(in) + up2(in2) + up3(in3))
     int cin = 0, cout = 0, k = 1, stride = 1, up = 1;
     int relu = 0;
     size_t w_off = 0;           // offset (in halfs) into the weight blob: layout [tap][cout][cin]
