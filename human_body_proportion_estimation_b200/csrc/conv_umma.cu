@@ -24,6 +24,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <cmath>
 
 // ---------------------------------------------------------------------------
 // driver entry point for tensor-map encoding (no link-time libcuda dependency)
@@ -65,16 +67,26 @@ struct ConvParams {
     const __half* res;
     __half* out;
     int n_tiles;                 // halo mode: tiles walked by the persistent CTAs (set at launch)
-    int acc_bufs;                // halo mode: 1 or 2 accumulator buffers in TMEM
+    int acc_bufs;                // halo mode: accumulator buffers in TMEM (always 2)
+    int a_stages;                // halo mode: halo tiles in flight (ring depth)
+    int b_slots;                 // halo mode: weight slots of three taps (one dx, dy = 0..2) each: 3*n_chunks when resident, else ring depth
+    int b_resident;              // halo mode: weights stay in shared memory for the CTA's lifetime
+    int res_smem;                // halo mode: residual tiles come through a TMA ring in shared memory (same stage index as the halo tile)
+    int r_chunks;                // residual boxes per tile (64 output channels each)
+    uint32_t r_chunk_bytes, r_box_bytes, r_row_bytes;
+    int issuers;                 // halo mode: MMA-issuing warps
+    int teams;                   // halo mode: epilogue teams (2 needs an even number of ring stages and accumulator buffers) (2: alternate tiles, one accumulator buffer each)
+    int dbg_flags;               // bring-up experiments: 1 = skip the output stores, 2 = skip the bias loads
     long long* dbg;              // optional phase timestamps (8 per CTA, first 64 CTAs), bring-up only
 };
 
 struct UmmaPlan {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmR;   // tmR: residual tensor (halo mode with res_smem)
     ConvParams prm;
     size_t smem_bytes;
     int n_splits;
     int occ;                     // resident CTAs per SM (halo mode: sizes the persistent grid)
+    int sm_budget;               // halo mode: SMs (= persistent CTAs) this launch may use
 };
 
 // ---------------------------------------------------------------------------
@@ -91,7 +103,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    // try_wait suspends in hardware for a bounded time; a pipeline that has not
+    // try_wait suspends the warp in hardware up to the time hint (it wakes on completion), so a
+    // waiting role does not take issue slots from the warps that share its scheduler; a pipeline that has not
     // advanced for ~2 s is a bug (wrong expect_tx byte count, bad tensor map):
     // trap instead of hanging the GPU.
     long long t0 = 0;
@@ -100,9 +113,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
         if (done) return;
         if ((spins & 1023u) == 1023u) {
             const long long now = clock64();
@@ -165,6 +178,13 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 __device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute
+// starts while its stream predecessor is still running; everything that does not touch the
+// predecessor's output (barrier init, TMEM allocation, weight / bias loads) runs ahead of
+// pdl_wait(), which returns once the predecessor grid has completed and flushed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -371,54 +391,81 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 constexpr int kHaloW = 10;       // 8 output columns + 1 halo column each side
 constexpr int kMaxChunks = 8;
+constexpr int kMaxAStages = 4;   // halo tiles in flight per CTA
+constexpr int kMaxBSlots = 24;   // (3 dx) x 8 Cin chunks: weight slots of three taps each (resident) or ring depth (streamed)
+constexpr int kHaloThreads = 384;   // warp 0 TMA, warps 1-3 MMA issuers (warp 1 owns TMEM), warps 4-7 / 8-11 two epilogue teams
+constexpr int kMaxAccBufs = 4;
+constexpr uint32_t kHaloBarBytes = 8u * (kMaxAStages * kMaxChunks + 3 * kMaxAStages + 2 * kMaxBSlots + 2 * kMaxAccBufs) + 16u;
 
-// 3x3 stride-1 convolution, halo mode, persistent CTAs.  Tile = tn images x th rows x 8
-// columns.  In shared memory a chunk is the TMA box (chunk channels, 10, rs = th+2, tn): pixel
-// rows of `row_bytes` ordered [n][h][w], i.e. "stacked" image rows q = n*rs + h of 10 pixels
-// each.  MMA row r of M-tile mt is pixel column r%8 of stacked row g = mt*16 + r/8; tap (dy,dx)
-// reads stacked row g+dy, column r%8+dx: a K-major operand with start offset
+// 3x3 stride-1 convolution, halo mode, one persistent CTA per SM.  Tile = tn images x th rows
+// x 8 columns.  In shared memory a chunk is the TMA box (chunk channels, 10, rs = th+2, tn):
+// pixel rows of `row_bytes` ordered [n][h][w], i.e. "stacked" image rows q = n*rs + h of 10
+// pixels each.  MMA row r of M-tile mt is pixel column r%8 of stacked row g = mt*16 + r/8; tap
+// (dy,dx) reads stacked row g+dy, column r%8+dx: a K-major operand with start offset
 // ((mt*16+dy)*10+dx)*row_bytes and an 8-row-group stride of 10 rows.  Stacked rows that are
 // halo rows (g % rs >= th) yield garbage accumulator rows which the epilogue skips.
 //
-// Each CTA walks tiles blockIdx.x, +gridDim.x, ... (grid = SMs x resident CTAs, so there is
-// no partial last wave).  The accumulator is double-buffered in TMEM when it fits
-// (p.acc_bufs == 2): the MMA lane starts tile j+1 while the epilogue warps drain tile j; the
-// producer refills the halo buffers as soon as tile j's MMAs have retired.  The residual and
-// the bias are fetched before the epilogue waits for the accumulator.
+// Pipeline (all phases of consecutive tiles overlap inside ONE CTA -- co-resident CTAs of one
+// launch run in lock step and do not hide each other's phases):
+//   * the halo tiles go through a ring of p.a_stages buffers: the producer warp runs up to
+//     a_stages tiles ahead of the MMA lane;
+//   * the weights of all nine taps stay resident in shared memory for the CTA's lifetime when
+//     they fit (p.b_resident), otherwise they stream through a deep ring of p.b_slots stages;
+//   * the accumulator is double-buffered in TMEM (p.acc_bufs == 2) and two teams of four
+//     epilogue warps drain alternate tiles while the MMA lane fills the other buffer;
+//   * the tensor pipe queues only ~2 MMAs, so every cycle the issuing lane spends on barrier
+//     waits, fences and commits between tiles idles the pipe: with resident weights TWO warps
+//     issue, tile j by warp j % issuers into accumulator buffer j % acc_bufs, and hide each
+//     other's per-tile overhead;
+//   * one warp saturates the tensor pipe with M=128 x N=32 MMAs (40 cycles each, shared-memory
+//     feed bound; tools/umma_rate_probe.cu) only if nothing but the MMAs sits in its issue
+//     path: the kernel is a template on (k-steps per chunk, M-tiles) and the MMAs of one weight
+//     slot (three taps) are straight-line code whose descriptors differ by immediates.
+// Each CTA walks tiles blockIdx.x, +gridDim.x, ... (grid <= SM count: no partial wave).
 constexpr int kResPrefetch = 8;   // uint4 (8 halfs) of residual a thread may hold in flight
 
-__global__ void __launch_bounds__(kThreads)
+template <int KSTEPS, int MT>
+__global__ void __launch_bounds__(kHaloThreads, 1)
 conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const ConvParams p) {
+                      const __grid_constant__ CUtensorMap tmR, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_tile_bytes = p.n_chunks * p.a_chunk_bytes;
     const uint32_t a_base = smem_base;
-    const uint32_t b_base = a_base + p.n_chunks * p.a_chunk_bytes;
-    const uint32_t bar_base = b_base + p.stages * p.b_stage_bytes;
-    const uint32_t a_full = bar_base;                                   // kMaxChunks x 8 B
-    const uint32_t b_full = a_full + 8u * kMaxChunks;
-    const uint32_t b_empty = b_full + 8u * p.stages;
-    const uint32_t acc_full = b_empty + 8u * p.stages;                  // 2 x 8 B
-    const uint32_t acc_empty = acc_full + 16u;                          // 2 x 8 B
-    const uint32_t tmem_slot = acc_empty + 16u;
-    float* s_bias = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));
+    const uint32_t b_base = a_base + p.a_stages * a_tile_bytes;
+    const uint32_t r_base = b_base + p.b_slots * 3u * p.b_stage_bytes;  // residual ring: a_stages x r_chunks x r_chunk_bytes
+    const uint32_t r_tile_bytes = p.res_smem ? p.r_chunks * p.r_chunk_bytes : 0u;
+    const uint32_t bar_base = r_base + p.a_stages * r_tile_bytes;
+    const uint32_t a_full = bar_base;                                   // a_stages x n_chunks
+    const uint32_t a_empty = a_full + 8u * (kMaxAStages * kMaxChunks);  // a_stages
+    const uint32_t b_full = a_empty + 8u * kMaxAStages;                 // b_slots
+    const uint32_t b_empty = b_full + 8u * kMaxBSlots;                  // b_slots (ring only)
+    const uint32_t acc_full = b_empty + 8u * kMaxBSlots;                // acc_bufs
+    const uint32_t acc_empty = acc_full + 8u * kMaxAccBufs;             // acc_bufs
+    const uint32_t res_full = acc_empty + 8u * kMaxAccBufs;             // a_stages
+    const uint32_t res_empty = res_full + 8u * kMaxAStages;             // a_stages
+    const uint32_t tmem_slot = res_empty + 8u * kMaxAStages;
+    float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + kHaloBarBytes - smem_u32(smem_raw)));
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int n_off = blockIdx.y * p.n_tile;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
-    long long* dbg = (p.dbg && blockIdx.x < 64 && blockIdx.y == 0) ? p.dbg + blockIdx.x * 32 : nullptr;
+    long long* dbg = (p.dbg && blockIdx.x < 64 && blockIdx.y == 0) ? p.dbg + blockIdx.x * 256 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+    pdl_launch_dependents();             // the next launch of this stream may start its prologue
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        for (int c = 0; c < p.n_chunks; ++c) mbar_init(a_full + 8u * c, 1);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(b_full + 8u * s, 1); mbar_init(b_empty + 8u * s, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8u * i, 1); mbar_init(acc_empty + 8u * i, 128); }
+        if (p.res_smem) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+        for (int i = 0; i < p.a_stages * p.n_chunks; ++i) mbar_init(a_full + 8u * i, 1);
+        for (int i = 0; i < p.a_stages; ++i) { mbar_init(a_empty + 8u * i, 1); mbar_init(res_full + 8u * i, 1); mbar_init(res_empty + 8u * i, 4); }
+        for (int i = 0; i < p.b_slots; ++i) { mbar_init(b_full + 8u * i, 1); mbar_init(b_empty + 8u * i, 1); }
+        for (int i = 0; i < kMaxAccBufs; ++i) { mbar_init(acc_full + 8u * i, 1); mbar_init(acc_empty + 8u * i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
-    for (int i = threadIdx.x; i < p.n_tile; i += kThreads) s_bias[i] = p.bias[n_off + i];
+    for (int i = threadIdx.x; i < p.n_tile; i += kHaloThreads) s_bias[i] = p.bias[n_off + i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -426,170 +473,305 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
-    const uint32_t acc_stride = (uint32_t)(p.m_tiles * p.n_tile);      // TMEM columns per accumulator buffer
+    const uint32_t acc_stride = (uint32_t)(MT * p.n_tile);              // TMEM columns per accumulator buffer
+    const uint32_t b_bytes = (uint32_t)p.n_tile * p.row_bytes;          // one tap; a slot holds three (dy = 0..2 of one dx)
+    const uint32_t b_slot_bytes = 3u * p.b_stage_bytes;
 
     if (warp == 0) {
         // ===== TMA producer (warp-wide control flow, one elected lane issues) =====
-        int s = 0, j = 0;
-        uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
-            const int tile_w = tile % p.tiles_w, tile_h = (tile / p.tiles_w) % p.tiles_h;
-            const int n0 = (tile / tiles_per_img) * p.tn, h0 = tile_h * p.th, w0 = tile_w * 8;
-            // the halo buffers are free once the previous tile's MMAs have retired
-            if (j > 0) mbar_wait(acc_full + 8u * ((j - 1) % p.acc_bufs), (uint32_t)(((j - 1) / p.acc_bufs) & 1));
+        const int T = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+        // halo tile t of this CTA -> ring stage t % a_stages; the stage is free once the MMAs of
+        // tile t - a_stages have retired (completion number t / a_stages - 1 of its a_empty barrier)
+        int atw, ath, atg;                       // coordinates of the next tile whose halo is requested
+        {
+            const int tile = (int)blockIdx.x;
+            atw = tile % p.tiles_w; ath = (tile / p.tiles_w) % p.tiles_h; atg = tile / tiles_per_img;
+        }
+        const int astep = (int)gridDim.x;
+        const int adw = astep % p.tiles_w, adh = (astep / p.tiles_w) % p.tiles_h, adg = astep / tiles_per_img;
+        int a_sa = 0, a_lap = 0;
+        auto issue_a = [&](int t) {             // called for t = 0, 1, 2, ... in order
+            (void)t;
+            const int sa = a_sa, lap = a_lap;
+            const int n0 = atg * p.tn, h0 = ath * p.th, w0 = atw * 8;
+            if (lap > 0) mbar_wait(a_empty + 8u * sa, (uint32_t)((lap - 1) & 1));
+            if (dbg && lane == 0 && t < 16) dbg[128 + t] = clock64();     // A(t) requested
             if (elect_one()) {
                 for (int cc = 0; cc < p.n_chunks; ++cc) {
-                    mbar_expect_tx(a_full + 8u * cc, p.a_box_bytes);
-                    tma_load_4d(a_base + cc * p.a_chunk_bytes, &tmA, a_full + 8u * cc, cc * p.chunk, w0 - 1, h0 - 1, n0);
+                    const uint32_t bar = a_full + 8u * (sa * p.n_chunks + cc);
+                    mbar_expect_tx(bar, p.a_box_bytes);
+                    tma_load_4d(a_base + sa * a_tile_bytes + cc * p.a_chunk_bytes, &tmA, bar, cc * p.chunk, w0 - 1, h0 - 1, n0);
                 }
             }
             __syncwarp();
-            for (int cc = 0; cc < p.n_chunks; ++cc)
-                for (int tap = 0; tap < 9; ++tap) {
-                    mbar_wait(b_empty + 8u * s, ph ^ 1u);
+            if (p.res_smem) {
+                // the residual rows of the same tile (no halo), 64 output channels per box
+                if (lap > 0) mbar_wait(res_empty + 8u * sa, (uint32_t)((lap - 1) & 1));
+                if (elect_one()) {
+                    mbar_expect_tx(res_full + 8u * sa, (uint32_t)p.r_chunks * p.r_box_bytes);
+                    for (int rc = 0; rc < p.r_chunks; ++rc)
+                        tma_load_4d(r_base + sa * r_tile_bytes + rc * p.r_chunk_bytes, &tmR, res_full + 8u * sa, n_off + rc * 64, w0, h0, n0);
+                }
+                __syncwarp();
+            }
+            if (++a_sa == p.a_stages) { a_sa = 0; ++a_lap; }
+            atw += adw; if (atw >= p.tiles_w) { atw -= p.tiles_w; ++ath; }
+            ath += adh; if (ath >= p.tiles_h) { ath -= p.tiles_h; ++atg; }
+            atg += adg;
+        };
+        // weights do not depend on the previous launch: request them before the dependency wait
+        if (p.b_resident) {
+            // all weights of this CTA's output-channel slice, once; one barrier per (chunk, tap)
+            // so that the first tile starts as soon as its first tap has landed
+            if (elect_one()) {
+                for (int cc = 0; cc < p.n_chunks; ++cc)
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int i = cc * 3 + dx;
+                        mbar_expect_tx(b_full + 8u * i, 3u * b_bytes);
+                        for (int dy = 0; dy < 3; ++dy)
+                            tma_load_2d(b_base + i * b_slot_bytes + dy * p.b_stage_bytes, &tmB, b_full + 8u * i, cc * p.chunk,
+                                        (dy * 3 + dx) * p.Cout + n_off);
+                    }
+            }
+            __syncwarp();
+        }
+        pdl_wait();                          // activations below are the previous launch's output
+        for (int t = 0; t < p.a_stages && t < T; ++t) issue_a(t);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int j = 0; j < T; ++j) {
+            if (!p.b_resident) {
+                for (int cc = 0; cc < p.n_chunks; ++cc)
+                    for (int dx = 0; dx < 3; ++dx) {
+                        mbar_wait(b_empty + 8u * s, ph ^ 1u);
+                        if (elect_one()) {
+                            mbar_expect_tx(b_full + 8u * s, 3u * b_bytes);
+                            for (int dy = 0; dy < 3; ++dy)
+                                tma_load_2d(b_base + s * b_slot_bytes + dy * p.b_stage_bytes, &tmB, b_full + 8u * s, cc * p.chunk,
+                                            (dy * 3 + dx) * p.Cout + n_off);
+                        }
+                        __syncwarp();
+                        if (++s == p.b_slots) { s = 0; ph ^= 1u; }
+                    }
+            }
+            if (j + p.a_stages < T) issue_a(j + p.a_stages);
+        }
+    } else if (warp <= 3) {
+      if (warp - 1 < p.issuers) {
+        // ===== MMA issuers (warp-wide control flow, one elected lane issues) =====
+        const int iss = warp - 1;
+        constexpr uint32_t kRow16 = KSTEPS * 2;                                 // one pixel row (chunk halfs) in 16-byte units
+        constexpr uint32_t kMtStep = 16u * kHaloW * kRow16;
+        const uint64_t da0 = make_desc(0, p.row_bytes, kHaloW * p.row_bytes);   // A: 8-row groups 10 rows apart
+        const uint64_t db0 = make_desc(0, p.row_bytes);
+        const uint32_t bstep = p.b_stage_bytes >> 4;                            // one tap of weights in 16-byte units
+        const uint32_t idesc = p.idesc, n_tile = (uint32_t)p.n_tile;
+        const int T = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+        int s = 0;
+        uint32_t ph = 0;
+        int sa = iss % p.a_stages, lap_a = iss / p.a_stages;      // halo stage / lap of tile j
+        int ab = iss % p.acc_bufs, use = iss / p.acc_bufs;        // accumulator buffer of tile j / how often it was filled before
+        for (int j = iss; j < T; j += p.issuers) {
+            const uint32_t pa = (uint32_t)(lap_a & 1);
+            // accumulator buffer `ab` must have been drained by the epilogue of its previous tile
+            if (use > 0) {
+                mbar_wait(acc_empty + 8u * ab, (uint32_t)((use - 1) & 1));
+                tc_fence_after();
+            }
+            const uint32_t d_base = tmem_base + ab * acc_stride;
+            if (dbg && lane == 0 && j < 16) dbg[32 + 3 * j] = clock64();        // accumulator free
+            for (int cc = 0; cc < p.n_chunks; ++cc) {
+                mbar_wait(a_full + 8u * (sa * p.n_chunks + cc), pa);
+                if (dbg && cc == 0 && j == 0 && lane == 0) dbg[2] = clock64();
+                if (dbg && cc == 0 && lane == 0 && j < 16) dbg[33 + 3 * j] = clock64();   // A landed
+                const uint64_t a_c = da0 + ((a_base + sa * a_tile_bytes + cc * p.a_chunk_bytes) >> 4);
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int slot = p.b_resident ? cc * 3 + dx : s;
+                    if (!p.b_resident) mbar_wait(b_full + 8u * s, ph);
+                    else if (j < p.issuers) mbar_wait(b_full + 8u * slot, 0);      // this warp's first tile
+                    if (dbg && cc == 0 && dx == 0 && j == 0 && lane == 0) dbg[3] = clock64();
+                    tc_fence_after();
+                    const uint64_t b_s = db0 + ((b_base + slot * b_slot_bytes) >> 4);
+                    const uint32_t fresh = (cc == 0 && dx == 0) ? 0u : 1u;      // first MMA of a tile overwrites
                     if (elect_one()) {
-                        mbar_expect_tx(b_full + 8u * s, (uint32_t)p.n_tile * p.row_bytes);
-                        tma_load_2d(b_base + s * p.b_stage_bytes, &tmB, b_full + 8u * s, cc * p.chunk, tap * p.Cout + n_off);
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint64_t bd = b_s + (uint32_t)dy * bstep;
+#pragma unroll
+                            for (int ks = 0; ks < KSTEPS; ++ks)
+#pragma unroll
+                                for (int mt = 0; mt < MT; ++mt)
+                                    umma_f16(d_base + mt * n_tile, a_c + (uint32_t)((dy * kHaloW + dx) * kRow16 + mt * kMtStep + 2 * ks),
+                                             bd + 2 * ks, idesc, (dy | ks) ? 1u : fresh);
+                        }
+                        if (!p.b_resident) umma_commit(b_empty + 8u * s);
                     }
                     __syncwarp();
-                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    if (!p.b_resident && ++s == p.b_slots) { s = 0; ph ^= 1u; }
                 }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer (warp-wide control flow, one elected lane issues) =====
-        {
-            const int ksteps = p.chunk / 16;
-            const uint64_t da0 = make_desc(0, p.row_bytes, kHaloW * p.row_bytes);   // A: 8-row groups 10 rows apart
-            const uint64_t db0 = make_desc(0, p.row_bytes);
-            const uint32_t row16 = p.row_bytes >> 4;                                // one pixel row in 16-byte units
-            const uint32_t mt_step = 16u * kHaloW * row16;
-            int s = 0, j = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
-                const int ab = j % p.acc_bufs;
-                // accumulator buffer `ab` must have been drained by the epilogue of tile j - acc_bufs
-                if (j >= p.acc_bufs) {
-                    mbar_wait(acc_empty + 8u * ab, (uint32_t)(((j - p.acc_bufs) / p.acc_bufs) & 1));
-                    tc_fence_after();
-                }
-                const uint32_t d_base = tmem_base + ab * acc_stride;
-                uint32_t first = 0;
-                for (int cc = 0; cc < p.n_chunks; ++cc) {
-                    mbar_wait(a_full + 8u * cc, (uint32_t)(j & 1));
-                    if (dbg && cc == 0 && j == 0 && lane == 0) dbg[2] = clock64();
-                    const uint64_t a_c = da0 + ((a_base + cc * p.a_chunk_bytes) >> 4);
-                    for (int dy = 0; dy < 3; ++dy)
-                        for (int dx = 0; dx < 3; ++dx) {
-                            mbar_wait(b_full + 8u * s, ph);
-                            if (dbg && !first && j == 0 && lane == 0) dbg[3] = clock64();
-                            if (dbg && j == 0 && cc == 0 && lane == 0) dbg[8 + dy * 3 + dx] = clock64();
-                            tc_fence_after();
-                            const uint64_t bd0 = db0 + ((b_base + s * p.b_stage_bytes) >> 4);
-                            const uint64_t a_t = a_c + (uint32_t)(dy * kHaloW + dx) * row16;
-                            if (elect_one()) {
-                                for (int mt = 0; mt < p.m_tiles; ++mt) {
-                                    const uint64_t ad = a_t + mt * mt_step;
-                                    const uint32_t dt = d_base + mt * p.n_tile;
-                                    umma_f16(dt, ad, bd0, p.idesc, first);
-                                    umma_f16(dt, ad + 2, bd0 + 2, p.idesc, 1u);
-                                    if (ksteps == 4) {
-                                        umma_f16(dt, ad + 4, bd0 + 4, p.idesc, 1u);
-                                        umma_f16(dt, ad + 6, bd0 + 6, p.idesc, 1u);
-                                    }
-                                }
-                                umma_commit(b_empty + 8u * s);
-                            }
-                            __syncwarp();
-                            first = 1u;
-                            if (dbg && j == 0 && cc == 0 && lane == 0) dbg[20 + dy * 3 + dx] = clock64();
-                            if (++s == p.stages) { s = 0; ph ^= 1u; }
-                        }
-                }
-                if (elect_one()) umma_commit(acc_full + 8u * ab);
-                __syncwarp();
-                if (dbg && j == 0 && lane == 0) dbg[4] = clock64();
             }
+            if (elect_one()) {
+                umma_commit(a_empty + 8u * sa);          // halo stage free when these MMAs retire
+                umma_commit(acc_full + 8u * ab);         // accumulator ready for its epilogue team
+            }
+            __syncwarp();
+            if (dbg && j == 0 && lane == 0) dbg[4] = clock64();
+            if (dbg && lane == 0 && j < 16) dbg[34 + 3 * j] = clock64();        // MMAs issued
+            sa += p.issuers; while (sa >= p.a_stages) { sa -= p.a_stages; ++lap_a; }
+            ab += p.issuers; while (ab >= p.acc_bufs) { ab -= p.acc_bufs; ++use; }
         }
+      }
     } else {
-        // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> global =====
-        const int grp = warp & 3;
+        // ===== epilogue teams: TMEM -> registers -> (+bias, +residual, ReLU) -> global =====
+        // Team t drains tiles t, t + teams, ... of this CTA.  An accumulator of <= 64 columns is
+        // copied to registers in one go and handed back to the MMA warps at once; the residual
+        // rows come from the TMA ring in shared memory (the producer requested them together with
+        // the tile's halo, several tiles ahead).  No integer division on the per-tile path: the row geometry of a thread is
+        // loop-invariant and the tile coordinates advance by a precomputed (dw, dh, dn) step.
+        const int team = (warp - 4) >> 2;
+        const int grp = warp & 3;                               // TMEM lane group this warp may read
         const int r = grp * 32 + lane;
-        const int chunks8 = p.n_tile >> 3;                      // uint4 per pixel row
-        const bool prefetch = p.res != nullptr && p.m_tiles * chunks8 <= kResPrefetch;
-        int j = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
-            const int tile_w = tile % p.tiles_w, tile_h = (tile / p.tiles_w) % p.tiles_h;
-            const int n0 = (tile / tiles_per_img) * p.tn, h0 = tile_h * p.th, w0 = tile_w * 8;
-            const int ab = j % p.acc_bufs;
-            bool valid[2];
-            size_t obase[2];
+        const bool has_res = p.res != nullptr;
+        const bool res_smem = p.res_smem != 0;
+        const uint32_t t_lane0 = tmem_base + ((uint32_t)(grp * 32) << 16);
+        const int teams = p.teams;
+        const int T = team < teams ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        // loop-invariant geometry of this thread's (up to two) accumulator rows
+        bool row_ok[2];
+        int row_n[2], row_w;
+        size_t row_off[2];
+        uint32_t rs_off[2], rs_xor[2];                 // residual ring: byte offset of this thread's row in a box, its swizzle term
+        row_w = r & 7;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int g = mt * 16 + (r >> 3);
+            const int nn = g / p.rs, hh = g - nn * p.rs;
+            row_ok[mt] = mt < MT && nn < p.tn && hh < p.th;
+            row_n[mt] = nn;
+            row_off[mt] = (((size_t)nn * p.Ho + hh) * p.Wo + row_w) * p.Cout + n_off;
+            const uint32_t rrow = row_ok[mt] ? (uint32_t)((nn * p.th + hh) * 8 + row_w) : 0u;   // box rows are ordered [n][h][w]
+            rs_off[mt] = rrow * p.r_row_bytes;
+            rs_xor[mt] = p.r_row_bytes == 128 ? (rrow & 7u) : ((rrow >> 1) & 3u);    // SWIZZLE_128B / SWIZZLE_64B on 1024-aligned boxes
+        }
+        // 16 residual halfs (two 16-byte chunks) of columns c0..c0+15 of this thread's row, from the ring stage at `rst`
+        auto res_lds = [&](uint32_t rst, int mt, int c0, uint4& q0, uint4& q1) {
+            const uint32_t box = rst + (uint32_t)(c0 >> 6) * p.r_chunk_bytes + rs_off[mt];
+            const uint32_t ci = (uint32_t)(c0 & 63) >> 3;
+            const uint32_t a0 = box + (((ci) ^ rs_xor[mt]) << 4), a1 = box + (((ci + 1) ^ rs_xor[mt]) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "r"(a0));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "r"(a1));
+        };
+        // tile walk: tile index -> (column tile, row tile, image group), advanced without divisions
+        int tw, th_, tg;
+        {
+            const int tile = (int)blockIdx.x + team * (int)gridDim.x;
+            tw = tile % p.tiles_w; th_ = (tile / p.tiles_w) % p.tiles_h; tg = tile / tiles_per_img;
+        }
+        const int step = teams * (int)gridDim.x;
+        const int dw = step % p.tiles_w, dh = (step / p.tiles_w) % p.tiles_h, dg = step / tiles_per_img;
+        bool valid[2];
+        size_t obase[2];
+        auto locate = [&]() {
+            const int n0 = tg * p.tn, h0 = th_ * p.th, w0 = tw * 8;
+            const size_t origin = (((size_t)n0 * p.Ho + h0) * p.Wo + w0) * p.Cout;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                const int g = mt * 16 + (r >> 3), col = r & 7;
-                const int nn = g / p.rs, hh = g - nn * p.rs;
-                const int n = n0 + nn, ho = h0 + hh, wo = w0 + col;
-                valid[mt] = mt < p.m_tiles && nn < p.tn && hh < p.th && n < p.P && wo < p.Wo;
-                obase[mt] = ((((size_t)n * p.Ho + ho) * p.Wo) + wo) * p.Cout + n_off;
+                valid[mt] = row_ok[mt] && n0 + row_n[mt] < p.P && w0 + row_w < p.Wo;
+                obase[mt] = origin + row_off[mt];
             }
-            uint4 rq[kResPrefetch];
-            if (prefetch) {
+        };
+        auto advance = [&]() {
+            tw += dw; if (tw >= p.tiles_w) { tw -= p.tiles_w; ++th_; }
+            th_ += dh; if (th_ >= p.tiles_h) { th_ -= p.tiles_h; ++tg; }
+            tg += dg;
+        };
+        // x = accumulator columns c0..c0+15 -> +bias (+residual q0|q1) -> ReLU -> fp16 -> global
+        auto finish16 = [&](const uint32_t* rr, size_t o, int c0, uint4 q0, uint4 q1) {
+            float x[16];
 #pragma unroll
-                for (int q = 0; q < kResPrefetch; ++q) {
-                    const int mt = q / chunks8, c8 = q - mt * chunks8;
-                    if (mt < p.m_tiles && valid[mt & 1])
-                        rq[q] = *reinterpret_cast<const uint4*>(p.res + obase[mt & 1] + c8 * 8);
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 b4 = (p.dbg_flags & 2) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q4);
+                x[4 * q4] = __uint_as_float(rr[4 * q4]) + b4.x; x[4 * q4 + 1] = __uint_as_float(rr[4 * q4 + 1]) + b4.y;
+                x[4 * q4 + 2] = __uint_as_float(rr[4 * q4 + 2]) + b4.z; x[4 * q4 + 3] = __uint_as_float(rr[4 * q4 + 3]) + b4.w;
+            }
+            if (has_res) {
+                const __half2* h0p = reinterpret_cast<const __half2*>(&q0);
+                const __half2* h1p = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f0 = __half22float2(h0p[q]), f1 = __half22float2(h1p[q]);
+                    x[2 * q] += f0.x; x[2 * q + 1] += f0.y;
+                    x[8 + 2 * q] += f1.x; x[8 + 2 * q + 1] += f1.y;
                 }
             }
-            mbar_wait(acc_full + 8u * ab, (uint32_t)((j / p.acc_bufs) & 1));
-            if (dbg && warp == 2 && lane == 0 && j == 0) dbg[5] = clock64();
+            if (p.relu) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) x[q] = fmaxf(x[q], 0.f);
+            }
+            __align__(16) __half2 pk[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pk[q] = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+            if ((p.dbg_flags & 1) && pk[0].x != __float2half(12345.f)) return;
+            *reinterpret_cast<uint4*>(p.out + o) = *reinterpret_cast<const uint4*>(&pk[0]);
+            *reinterpret_cast<uint4*>(p.out + o + 8) = *reinterpret_cast<const uint4*>(&pk[4]);
+        };
+
+        pdl_wait();                          // residual reads and output writes follow the previous launch
+        if (team < T) {
+            locate();
+        }
+        int sr = team % p.a_stages, lap_r = team / p.a_stages;      // ring stage / lap of tile j
+        const int groups = (MT * p.n_tile + 31) >> 5;               // 32-column groups of the accumulator buffer
+        for (int j = team; j < T; j += teams) {
+            const int abuf = j % p.acc_bufs, k = j / p.acc_bufs;
+            const uint32_t t_lane = t_lane0 + abuf * acc_stride;
+            const bool more = j + teams < T;
+            const uint32_t rst = r_base + sr * r_tile_bytes;
+            if (res_smem) mbar_wait(res_full + 8u * sr, (uint32_t)(lap_r & 1));
+            mbar_wait(acc_full + 8u * abuf, (uint32_t)(k & 1));
+            if (dbg && warp == 4 && lane == 0 && j == 0) dbg[5] = clock64();
+            if (dbg && grp == 2 && lane == 0 && j < 16) dbg[96 + 2 * j] = clock64();             // accumulator ready
             tc_fence_after();
-            for (int mt = 0; mt < p.m_tiles; ++mt) {
-                for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-                    uint32_t rr[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(grp * 32) << 16) + ab * acc_stride + (uint32_t)(mt * p.n_tile + c0), rr);
-                    tmem_ld_wait();
-                    if (!valid[mt]) continue;
-                    float x[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) x[q] = __uint_as_float(rr[q]) + s_bias[c0 + q];
-                    const size_t o = obase[mt] + c0;
-                    if (p.res) {
-                        uint4 q0, q1;
-                        if (prefetch) {
-                            const int qi = mt * chunks8 + (c0 >> 3);
-                            // constant-index selects keep rq[] in registers
-                            q0 = rq[0]; q1 = rq[1];
-#pragma unroll
-                            for (int t = 0; t < kResPrefetch; t += 2)
-                                if (t == qi) { q0 = rq[t]; q1 = rq[t + 1]; }
-                        } else {
-                            q0 = *reinterpret_cast<const uint4*>(p.res + o);
-                            q1 = *reinterpret_cast<const uint4*>(p.res + o + 8);
-                        }
-                        const __half2* h0p = reinterpret_cast<const __half2*>(&q0);
-                        const __half2* h1p = reinterpret_cast<const __half2*>(&q1);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float2 f0 = __half22float2(h0p[q]), f1 = __half22float2(h1p[q]);
-                            x[2 * q] += f0.x; x[2 * q + 1] += f0.y;
-                            x[8 + 2 * q] += f1.x; x[8 + 2 * q + 1] += f1.y;
-                        }
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) x[q] = fmaxf(x[q], 0.f);
-                    }
-                    __align__(16) __half2 pk[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) pk[q] = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
-                    *reinterpret_cast<uint4*>(p.out + o) = *reinterpret_cast<const uint4*>(&pk[0]);
-                    *reinterpret_cast<uint4*>(p.out + o + 8) = *reinterpret_cast<const uint4*>(&pk[4]);
+            for (int g = 0; g < groups; ++g) {
+                // 32 accumulator columns -> registers; after the last group the TMEM buffer goes back to the MMA warps
+                const int col = g << 5;
+                const int mt = MT == 1 ? 0 : (col >= p.n_tile ? 1 : 0);
+                const int c0 = col - mt * p.n_tile;
+                const bool two = c0 + 32 <= p.n_tile;
+                uint32_t ra[16], rb[16];
+                tmem_ld16(t_lane + (uint32_t)col, ra);
+                if (two) tmem_ld16(t_lane + (uint32_t)(col + 16), rb);
+                tmem_ld_wait();
+                if (g == groups - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty + 8u * abuf) : "memory");      // one arrival per epilogue warp
+                }
+                uint4 q[4] = {};
+                if (res_smem) {
+                    res_lds(rst, mt, c0, q[0], q[1]);
+                    if (two) res_lds(rst, mt, c0 + 16, q[2], q[3]);
+                } else if (has_res && valid[mt]) {          // residual straight from global memory (shapes the ring does not cover)
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.res + obase[mt] + c0);
+                    q[0] = rp[0]; q[1] = rp[1];
+                    if (two) { q[2] = rp[2]; q[3] = rp[3]; }
+                }
+                if (valid[mt]) {
+                    finish16(ra, obase[mt] + c0, c0, q[0], q[1]);
+                    if (two) finish16(rb, obase[mt] + c0 + 16, c0 + 16, q[2], q[3]);
                 }
             }
-            // this thread's TMEM reads of buffer `ab` are complete: hand it back to the MMA lane
-            tc_fence_before();
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty + 8u * ab) : "memory");
-            if (dbg && warp == 2 && lane == 0 && j == 0) dbg[6] = clock64();
+            if (res_smem) {
+                // residual stage back to the producer
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(res_empty + 8u * sr) : "memory");
+            }
+            if (dbg && warp == 4 && lane == 0 && j == 0) dbg[6] = clock64();
+            if (dbg && grp == 2 && lane == 0 && j < 16) dbg[97 + 2 * j] = clock64();             // epilogue done
+            // residual of this team's next tile: in flight while the team waits for that accumulator
+            if (more) { advance(); locate(); }
+            sr += teams; while (sr >= p.a_stages) { sr -= p.a_stages; ++lap_r; }
         }
     }
     tc_fence_before();
@@ -599,25 +781,6 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         tmem_dealloc(tmem_base, p.tmem_cols);
         if (dbg && lane == 0) dbg[7] = clock64();
     }
-}
-
-// halo tile shape for an Ho x Wo map: tn images x th rows (x 8 columns), m_tiles M-tiles.
-// Returns the fraction of MMA rows that are real output pixels (rows only; columns add Wo/(8*ceil(Wo/8))).
-double pick_halo_tile(int Ho, int* tn, int* th, int* m_tiles) {
-    double best = 0;
-    for (int m = 2; m >= 1; --m)                                // ties go to two M-tiles (weights shared)
-        for (int n = 1; n <= 6; ++n)
-            for (int h = Ho < 16 * m ? Ho : 16 * m; h >= 1; --h) {
-                if (Ho % h) continue;
-                if (n > 1 && h != Ho) continue;                 // stacked images need whole images
-                const int rs = h + 2;
-                // all groups of the tile must be covered: 16m >= n*rs - 2, and the reads stay in the buffer
-                if (16 * m < n * rs - 2) continue;
-                const double frac = (double)(n * h) / (16.0 * m);
-                if (frac > best + 1e-9) { best = frac; *tn = n; *th = h; *m_tiles = m; }
-                break;                                          // largest h for this (m, n)
-            }
-    return best;
 }
 
 int halo_mode_enabled() {
@@ -688,90 +851,156 @@ static int encode_weights_map(EncodeTiledFn enc, UmmaPlan* pl, const HrnetModel&
     return HBP_OK;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 // halo-mode plan (3x3, stride 1).  Returns HBP_OK with *ok = false when the shape does not fit.
 static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaPlan* pl, bool* ok) {
+    // SMs this launch may occupy (one persistent CTA each): the whole GPU, or the share of its
+    // resolution branch when the branches of a stage run side by side on their own streams
+    int sm_budget = op.sm_share > 0.f ? (int)(op.sm_share * ctx->sm_count + 0.5f) : ctx->sm_count;
+    if (env_int("HBP_HALO_SMS", 0)) sm_budget = env_int("HBP_HALO_SMS", 0);
+    if (sm_budget < 1) sm_budget = 1;
+    if (sm_budget > ctx->sm_count) sm_budget = ctx->sm_count;
     *ok = false;
     const HTensor& ti = m.tensors[op.in];
     const int Ho = ti.h, Wo = ti.w;
     ConvParams& p = pl->prm;
-    int tn = 1, th = 0, m_tiles = 1;
-    const double frac = pick_halo_tile(Ho, &tn, &th, &m_tiles);
-    if (frac < 0.5) return HBP_OK;
     const int chunk = op.cin == 32 ? 32 : 64, n_chunks = op.cin / chunk;
     if (n_chunks > kMaxChunks) return HBP_OK;
     const uint32_t row_bytes = chunk * 2;
-    const int tiles_w = (Wo + 7) / 8, tiles_h = Ho / th;
-    int n_tile = 0;
-    for (int c = op.cout < 256 ? op.cout : 256; c >= 16; c -= 16)
-        if (op.cout % c == 0 && m_tiles * c <= 512) { n_tile = c; break; }
-    if (!n_tile) return HBP_OK;
-    // prefer one M-tile when two would leave SMs idle
-    long tiles = (long)((capP + tn - 1) / tn) * tiles_h * tiles_w;
-    if (m_tiles == 2 && tn == 1 && th == 32 && tiles * (op.cout / n_tile) < 2L * ctx->sm_count) { th = 16; m_tiles = 1; }
-    // tiles are scarce (low-resolution branches at small batch): latency per CTA matters more than
-    // the share of useful MMA rows -- take the smallest tile (one image, one M-tile)
-    if (tiles * (op.cout / n_tile) < ctx->sm_count && (tn > 1 || m_tiles > 1)) {
-        tn = 1; m_tiles = 1;
-        th = Ho < 16 ? Ho : 16;
-        while (Ho % th) --th;
+    const int tiles_w = (Wo + 7) / 8;
+    const int sms = sm_budget;
+    const uint32_t budget = (uint32_t)env_int("HBP_HALO_SMEM_KB", 200) * 1024u;
+
+    // Candidate tiles: (tn images x th rows, m M-tiles).  One persistent CTA per SM walks
+    // ceil(items / SMs) work items of 16*m stacked 8-pixel rows each, so the time of the launch
+    // is ~ rounds * m * (MMA time of one M-tile) / (share of useful MMA rows is already inside
+    // `items`): pick the (tile, N split) with the fewest M-tile rounds; ties go to the larger N
+    // tile (fewer shared-memory bytes per MAC), then to the larger M (weights reused).
+    struct Cand { int tn, th, m, n_tile; long items; double cost; };
+    Cand best{0, 0, 0, 0, 0, 1e30};
+    for (int mt = 1; mt <= 2; ++mt)
+        for (int n = 1; n <= 6; ++n)
+            for (int h = Ho < 16 * mt ? Ho : 16 * mt; h >= 1; --h) {
+                if (Ho % h) continue;
+                if (n > 1 && h != Ho) continue;                 // stacked images need whole images
+                const int rs = h + 2;
+                if (16 * mt < n * rs - 2) continue;             // every group of the tile inside the M-tiles
+                if (n * h * 2 < 16 * mt && !(n == 1 && h == Ho)) { break; }   // < 50 % useful rows: only if nothing else
+                const long tiles = (long)((capP + n - 1) / n) * (Ho / h) * tiles_w;
+                for (int c = op.cout < 256 ? op.cout : 256; c >= 32; c -= 16) {
+                    if (op.cout % c || mt * c > 512) continue;
+                    const long items = tiles * (op.cout / c);
+                    const long rounds = (items + sms - 1) / sms;
+                    // cycles of one M-tile pass over all taps: max(tensor floor, shared-memory feed)
+                    const double per_mma = std::max(c / 2.0, (128.0 * 32 + c * 32.0) / 128.0);
+                    const double mma_cyc = (double)rounds * mt * per_mma * 9 * (op.cin / 16);
+                    // weight bytes one CTA pulls from L2 (~24 B/clk/SM when every SM streams): once when
+                    // they can stay resident, once per tile otherwise
+                    const double w_bytes = 9.0 * op.cin * c * 2;
+                    const bool fits = w_bytes + 2.0 * (16 * mt + 2) * kHaloW * op.cin * 2 < 190e3;
+                    const double w_cyc = (fits ? 1.0 : (double)rounds) * w_bytes / 24.0;
+                    const double cost = std::max(mma_cyc, w_cyc);
+                    const bool better = cost < best.cost * 0.97 ||
+                                        (cost < best.cost * 1.03 && (c > best.n_tile || (c == best.n_tile && mt > best.m)));
+                    if (better) best = Cand{n, h, mt, c, items, cost};
+                }
+                break;                                          // largest h for this (m, n)
+            }
+    if (!best.m) return HBP_OK;
+    int tn = best.tn, th = best.th, m_tiles = best.m, n_tile = best.n_tile;
+    if (env_int("HBP_HALO_M", 0)) {                             // bring-up override: force the M-tile count
+        const int fm = env_int("HBP_HALO_M", 0);
+        int ftn = 1, fth = 0, fmm = fm;
+        (void)fmm;
+        for (int h = Ho < 16 * fm ? Ho : 16 * fm; h >= 1; --h) if (Ho % h == 0) { fth = h; break; }
+        if (fth) { tn = ftn; th = fth; m_tiles = fm; }
     }
-    const int tiles_h2 = Ho / th;
-    tiles = (long)((capP + tn - 1) / tn) * tiles_h2 * tiles_w;
-    long ctas = tiles * (op.cout / n_tile);
-    while (ctas < ctx->sm_count && n_tile % 32 == 0 && n_tile > 32) { n_tile /= 2; ctas *= 2; }
+    if (env_int("HBP_HALO_N", 0) && op.cout % env_int("HBP_HALO_N", 0) == 0) n_tile = env_int("HBP_HALO_N", 0);
+    const int tiles_h = Ho / th;
     const int rs = th + 2;
+    const long tiles = (long)((capP + tn - 1) / tn) * tiles_h * tiles_w;
+    const int n_splits = op.cout / n_tile;
+    const long per_cta = (tiles * n_splits + sms - 1) / sms;            // tiles one CTA walks
+
     const uint32_t a_box_bytes = (uint32_t)(kHaloW * rs * tn) * row_bytes;
     uint32_t a_chunk_bytes = (uint32_t)((16 * m_tiles + 2) * kHaloW) * row_bytes;
     if (a_chunk_bytes < a_box_bytes) a_chunk_bytes = a_box_bytes;
     a_chunk_bytes = (a_chunk_bytes + 1023u) & ~1023u;
     const uint32_t b_stage = ((uint32_t)n_tile * row_bytes + 1023u) & ~1023u;
-    const uint32_t a_total = a_chunk_bytes * n_chunks;
-    const int k_iters = 9 * n_chunks;
-    int stages = 8;
-    if (stages > k_iters) stages = k_iters;
-    while (stages > 2 && a_total + stages * b_stage > 200 * 1024) --stages;
-    if (a_total + stages * b_stage > 200 * 1024) return HBP_OK;
-    // small CTAs: keep shared memory low enough for >= 3 CTAs per SM
-    while (stages > 4 && a_total + stages * b_stage > 72 * 1024) --stages;
+    // residual through shared memory: one TMA box of 64 (or 32) channels x the tile's pixels per stage,
+    // in the swizzle that makes the epilogue's 16-byte row reads conflict-free
+    const int r_ch = n_tile < 64 ? n_tile : 64;
+    const bool res_smem = op.res >= 0 && env_int("HBP_HALO_RES_SMEM", 1) && (r_ch == 32 || r_ch == 64) && n_tile % r_ch == 0;
+    const int r_chunks = res_smem ? n_tile / r_ch : 0;
+    const uint32_t r_row_bytes = (uint32_t)r_ch * 2;
+    const uint32_t r_box_bytes = (uint32_t)(8 * th * tn) * r_row_bytes;
+    const uint32_t r_chunk_bytes = (r_box_bytes + 1023u) & ~1023u;
+    const uint32_t a_tile = a_chunk_bytes * n_chunks + (res_smem ? r_chunks * r_chunk_bytes : 0u);     // one ring stage: halo tile + residual tile
+    const uint32_t fixed = kHaloBarBytes + (uint32_t)n_tile * 4 + 1024 + 64;
+    const int k_slots = 3 * n_chunks;                                   // weight slots per tile: (chunk, dx), three taps each
+    const uint32_t b_slot = 3u * b_stage;
+    const uint32_t b_all = (uint32_t)k_slots * b_slot;
+    int want_a = (int)std::min<long>(per_cta, env_int("HBP_HALO_ASTAGES", 4));
+    if (want_a < 1) want_a = 1;
+    if (want_a > kMaxAStages) want_a = kMaxAStages;
+    // resident weights when they fit beside at least min(2, want_a) halo stages
+    int a_stages = 0, b_slots = 0, resident = 0;
+    if (env_int("HBP_HALO_RESIDENT", 1) && fixed + b_all + a_tile <= budget) {
+        int fit = (int)((budget - fixed - b_all) / a_tile);
+        if (fit >= std::min(2, want_a)) { resident = 1; a_stages = std::min(fit, want_a); b_slots = k_slots; }
+    }
+    if (!resident) {
+        a_stages = std::min(want_a, 2);
+        while (a_stages > 1 && fixed + a_stages * a_tile + 3 * b_slot > budget) --a_stages;
+        if (fixed + a_stages * a_tile + 2 * b_slot > budget) return HBP_OK;
+        b_slots = (int)((budget - fixed - a_stages * a_tile) / b_slot);
+        if (b_slots > k_slots * (int)std::min<long>(per_cta, 2)) b_slots = k_slots * (int)std::min<long>(per_cta, 2);
+        if (b_slots > kMaxBSlots) b_slots = kMaxBSlots;
+        if (b_slots < 2) return HBP_OK;
+    }
+    if (a_stages == 3) a_stages = 2;         // even ring depth (see the note on parity waits below)
+    // accumulator double-buffered in TMEM whenever two buffers fit
+    int acc_bufs = 4 * m_tiles * n_tile <= 512 ? 4 : (2 * m_tiles * n_tile <= 512 ? 2 : 1);
+    if (env_int("HBP_HALO_BUFS", 0)) acc_bufs = env_int("HBP_HALO_BUFS", 0);
+    if (acc_bufs * m_tiles * n_tile > 512) return HBP_OK;
     if (kHaloW > 256 || rs > 256 || tn > 256) return HBP_OK;
 
     p.Ho = Ho; p.Wo = Wo; p.Cout = op.cout; p.up = 1; p.relu = op.relu;
     p.tn = tn; p.th = th; p.tw = 8; p.m_tiles = m_tiles; p.n_tile = n_tile;
     p.chunk = chunk; p.n_chunks = n_chunks; p.ksz = 3; p.stride = 1;
-    p.tiles_w = tiles_w; p.tiles_h = tiles_h2;
+    p.tiles_w = tiles_w; p.tiles_h = tiles_h;
     p.row_bytes = row_bytes;
     p.a_stage_bytes = 0; p.b_stage_bytes = b_stage; p.tx_bytes = 0;
-    p.stages = stages;
-    p.acc_bufs = 2 * m_tiles * n_tile <= 256 ? 2 : 1;
+    p.stages = b_slots;
+    p.res_smem = res_smem ? 1 : 0; p.r_chunks = r_chunks; p.r_chunk_bytes = r_chunk_bytes; p.r_box_bytes = r_box_bytes;
+    p.r_row_bytes = r_row_bytes;
+    p.dbg_flags = env_int("HBP_HALO_DBG", 0);
+    // Every mbarrier is waited on by parity, so a waiter must never run two phases ahead of it: ring
+    // stage s and accumulator buffer b are always served by the same issuer warp / epilogue team,
+    // i.e. the issuer and team counts divide the stage and buffer counts.
+    p.teams = (acc_bufs % 2 == 0 && a_stages % 2 == 0) ? 2 : 1;
+    p.issuers = (resident && p.teams == 2 && per_cta > 1) ? env_int("HBP_HALO_ISSUERS", 2) : 1;
+    if (a_stages % p.issuers || acc_bufs % p.issuers) p.issuers = 1;
+    p.acc_bufs = acc_bufs; p.a_stages = a_stages; p.b_slots = b_slots; p.b_resident = resident;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(p.acc_bufs * m_tiles * n_tile)) cols *= 2;
+    while (cols < (uint32_t)(acc_bufs * m_tiles * n_tile)) cols *= 2;
     p.tmem_cols = cols;
     p.idesc = (1u << 4) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     p.mode = 1; p.rs = rs; p.a_chunk_bytes = a_chunk_bytes; p.a_box_bytes = a_box_bytes;
     p.bias = m.d_bias + op.b_off;
     p.res = op.res >= 0 ? m.bufs[m.tensors[op.res].buf] : nullptr;
     p.out = m.bufs[m.tensors[op.out].buf];
-    pl->smem_bytes = (size_t)a_total + (size_t)stages * b_stage + 8 * kMaxChunks + 16 * stages + 64 + (size_t)n_tile * 4 + 1024;
-    pl->n_splits = op.cout / n_tile;
-    {
-        // resident CTAs per SM: registers, shared memory (+1 KB the runtime reserves per CTA),
-        // threads and TMEM columns
-        cudaFuncAttributes fa;
-        int regs = 80;
-        if (cudaFuncGetAttributes(&fa, conv_umma_halo_kernel) == cudaSuccess && fa.numRegs > 0) regs = fa.numRegs;
-        const int regs_per_cta = ((regs + 7) / 8 * 8) * kThreads;
-        int occ = 65536 / regs_per_cta;
-        const int by_smem = (int)((227 * 1024) / (pl->smem_bytes + 1024));
-        const int by_threads = 2048 / kThreads;
-        const int by_tmem = 512 / (int)cols;
-        if (occ > by_smem) occ = by_smem;
-        if (occ > by_threads) occ = by_threads;
-        if (occ > by_tmem) occ = by_tmem;
-        pl->occ = occ < 1 ? 1 : occ;
-        if (getenv("HBP_CONV_TRACE"))
-            fprintf(stderr, "[plan] %s halo tile tn=%d th=%d m=%d n_tile=%d stages=%d acc_bufs=%d tmem=%u regs=%d smem=%zu occ=%d\n",
-                    op.name.c_str(), tn, th, m_tiles, n_tile, stages, p.acc_bufs, cols, regs, pl->smem_bytes, pl->occ);
-    }
+    pl->smem_bytes = (size_t)a_stages * a_tile + (size_t)b_slots * b_slot + fixed;
+    pl->n_splits = n_splits;
+    pl->occ = 1;
+    pl->sm_budget = sm_budget;
+    if (getenv("HBP_CONV_TRACE"))
+        fprintf(stderr, "[plan] %s halo tile tn=%d th=%d m=%d n_tile=%d acc_bufs=%d a_stages=%d b_slots=%d resident=%d tmem=%u smem=%zu tiles=%ld per_cta=%ld sms=%d\n",
+                op.name.c_str(), tn, th, m_tiles, n_tile, acc_bufs, a_stages, b_slots, resident, cols, pl->smem_bytes, tiles, per_cta, sm_budget);
 
     EncodeTiledFn enc = get_encode();
     const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -786,6 +1015,20 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
         hbp_set_error("cuTensorMapEncodeTiled(A halo) failed (%d) for %s box=(%d,%d,%d,%d)", (int)r, op.name.c_str(),
                       chunk, kHaloW, rs, tn);
         return HBP_ERR_CUDA;
+    }
+    pl->tmR = pl->tmA;                       // placeholder when the residual does not go through shared memory
+    if (res_smem) {
+        const HTensor& tr = m.tensors[op.res];
+        cuuint64_t rdim[4] = {(cuuint64_t)tr.c, (cuuint64_t)tr.w, (cuuint64_t)tr.h, (cuuint64_t)capP};
+        cuuint64_t rstr[3] = {(cuuint64_t)tr.c * 2, (cuuint64_t)tr.w * tr.c * 2, (cuuint64_t)tr.h * tr.w * tr.c * 2};
+        cuuint32_t rbox[4] = {(cuuint32_t)r_ch, 8u, (cuuint32_t)th, (cuuint32_t)tn};
+        CUresult rr = enc(&pl->tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, m.bufs[tr.buf], rdim, rstr, rbox, est,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, r_ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rr != CUDA_SUCCESS) {
+            hbp_set_error("cuTensorMapEncodeTiled(residual) failed (%d) for %s box=(%d,8,%d,%d)", (int)rr, op.name.c_str(), r_ch, th, tn);
+            return HBP_ERR_CUDA;
+        }
     }
     int st = encode_weights_map(enc, pl, m, op, chunk, n_tile, sw);
     if (st) return st;
@@ -804,7 +1047,10 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     if (!enc) { delete pl; hbp_set_error("cuTensorMapEncodeTiled unavailable"); return HBP_ERR_CUDA; }
     if (!(ctx->attr_flags & ATTR_UMMA)) {
         HBP_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         ctx->attr_flags |= ATTR_UMMA;
     }
     if (op.k == 3 && op.stride == 1 && op.up == 1 && halo_mode_enabled()) {
@@ -893,6 +1139,21 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     return HBP_OK;
 }
 
+static void launch_halo(dim3 grid, size_t smem, cudaStream_t st, const UmmaPlan* pl, const ConvParams& p) {
+    static const int pdl = env_int("HBP_PDL", 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kHaloThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    const int ks = p.chunk / 16;
+    if (ks == 2 && p.m_tiles == 1) cudaLaunchKernelEx(&cfg, conv_umma_halo_kernel<2, 1>, pl->tmA, pl->tmB, pl->tmR, p);
+    else if (ks == 2) cudaLaunchKernelEx(&cfg, conv_umma_halo_kernel<2, 2>, pl->tmA, pl->tmB, pl->tmR, p);
+    else if (p.m_tiles == 1) cudaLaunchKernelEx(&cfg, conv_umma_halo_kernel<4, 1>, pl->tmA, pl->tmB, pl->tmR, p);
+    else cudaLaunchKernelEx(&cfg, conv_umma_halo_kernel<4, 2>, pl->tmA, pl->tmB, pl->tmR, p);
+}
+
 int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, cudaStream_t st) {
     (void)m; (void)op_index;
     ConvParams p = pl->prm;
@@ -900,43 +1161,50 @@ int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, 
     const int tiles_n = (P + p.tn - 1) / p.tn;
     dim3 grid((unsigned)(tiles_n * p.tiles_h * p.tiles_w), (unsigned)pl->n_splits);
     if (p.mode == 1) {
-        // persistent CTAs: one full wave, every CTA strides over the tiles
+        // one persistent CTA per SM: every CTA walks ceil(n_tiles / ctas) or one fewer tiles
         p.n_tiles = (int)grid.x;
-        int slots = ctx->sm_count * pl->occ / pl->n_splits;
+        int slots = pl->sm_budget / pl->n_splits;
         if (slots < 1) slots = 1;
         if ((int)grid.x > slots) {
-            // equalise: every CTA walks ceil(n_tiles / ctas) or one fewer tiles
             const int per = (p.n_tiles + slots - 1) / slots;
             grid.x = (unsigned)((p.n_tiles + per - 1) / per);
         }
     }
     static const bool trace = getenv("HBP_CONV_TRACE") != nullptr;
-    if (trace && p.mode == 1) {
-        static int traced = 0;
-        if (traced++ % 8 == 3) {        // a warm launch of every shape the process runs
+    cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+    if (trace) cudaStreamIsCapturing(st, &cap_status);
+    if (trace && p.mode == 1 && cap_status == cudaStreamCaptureStatusNone) {
+        {                               // every eager launch (the timed launches run inside a graph capture)
             long long* d = nullptr;
-            cudaMalloc(&d, 64 * 32 * sizeof(long long));
-            cudaMemset(d, 0, 64 * 32 * sizeof(long long));
+            cudaMalloc(&d, 64 * 256 * sizeof(long long));
+            cudaMemset(d, 0, 64 * 256 * sizeof(long long));
+            launch_halo(grid, pl->smem_bytes, st, pl, p);    // warm L2
             p.dbg = d;
-            conv_umma_halo_kernel<<<grid, kThreads, pl->smem_bytes, st>>>(pl->tmA, pl->tmB, p);
+            launch_halo(grid, pl->smem_bytes, st, pl, p);
             cudaStreamSynchronize(st);
-            static long long h[64 * 32];
+            static long long h[64 * 256];
             cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
             cudaFree(d);
             const int n = grid.x < 64 ? (int)grid.x : 64;
-            double acc[32] = {0};
-            for (int i = 0; i < n; ++i) for (int k = 1; k < 32; ++k) acc[k] += (double)(h[i * 32 + k] - h[i * 32]);
-            fprintf(stderr, "[taps] B landed / MMAs issued per tap (cycles from CTA start):");
-            for (int k = 0; k < 9; ++k) fprintf(stderr, " %.0f/%.0f", acc[8 + k] / n, acc[20 + k] / n);
-            fprintf(stderr, "\n");
+            double acc[8] = {0};
+            for (int i = 0; i < n; ++i) for (int k = 1; k < 8; ++k) acc[k] += (double)(h[i * 256 + k] - h[i * 256]);
             fprintf(stderr, "[trace] grid=(%u,%u) smem=%zu stages=%d m=%d n_tile=%d chunks=%d | cycles from CTA start: setup %.0f, A0 landed %.0f, "
                     "B0 landed %.0f, MMAs issued %.0f, accum ready %.0f, epilogue done %.0f, dealloc %.0f\n", grid.x, grid.y, pl->smem_bytes,
                     p.stages, p.m_tiles, p.n_tile, p.n_chunks, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n, acc[6] / n, acc[7] / n);
+            // timeline of CTA 0, cycles from its start: per tile j the MMA warp's (accumulator free, A landed, MMAs issued),
+            // the epilogue's (accumulator ready, done) and when the producer requested the halo
+            fprintf(stderr, "[timeline] tile: A requested | acc free, A landed, issued | epilogue ready, done\n");
+            for (int j = 0; j < 16; ++j) {
+                auto rel = [&](int k) { return h[k] ? (long long)(h[k] - h[0]) : -1LL; };
+                if (!h[34 + 3 * j]) break;
+                fprintf(stderr, "[timeline] %2d: %6lld | %6lld %6lld %6lld | %6lld %6lld\n", j, rel(128 + j), rel(32 + 3 * j), rel(33 + 3 * j),
+                        rel(34 + 3 * j), rel(96 + 2 * j), rel(97 + 2 * j));
+            }
             p.dbg = nullptr;
             return HBP_OK;
         }
     }
-    if (p.mode == 1) conv_umma_halo_kernel<<<grid, kThreads, pl->smem_bytes, st>>>(pl->tmA, pl->tmB, p);
+    if (p.mode == 1) launch_halo(grid, pl->smem_bytes, st, pl, p);
     else conv_umma_kernel<<<grid, kThreads, pl->smem_bytes, st>>>(pl->tmA, pl->tmB, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return hbp_cuda_fail(e, "conv_umma_kernel", __FILE__, __LINE__);

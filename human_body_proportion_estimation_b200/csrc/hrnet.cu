@@ -111,12 +111,27 @@ void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const
                   bool multi_scale_output) {
     HrnetModel& m = B.m;
     const int nb = (int)x.size();
+    // The branches run side by side, one stream each.  HBP_BRANCH_SHARE=a,b,c,d gives every branch's
+    // persistent conv launches a fixed share of the SMs so that the launches are resident at once;
+    // measured slower than letting every launch take the whole GPU (profiles/r01_branch_share.log),
+    // so the default (0) is no partition.
+    float share[4] = {0.f, 0.f, 0.f, 0.f};
+    if (const char* e = getenv("HBP_BRANCH_SHARE")) {
+        float v[4] = {0, 0, 0, 0};
+        if (sscanf(e, "%f,%f,%f,%f", &v[0], &v[1], &v[2], &v[3]) >= nb) {
+            float tot = 0;
+            for (int i = 0; i < nb; ++i) tot += v[i];
+            for (int i = 0; i < nb; ++i) share[i] = v[i] / tot;
+        }
+    }
     for (int i = 0; i < nb; ++i) {
         B.cur_stream = i;
         for (int blk = 0; blk < 4; ++blk) {
             const std::string p = pre + S(".branches.%d.%d", i, blk);
             const int t = B.conv(p + ".conv1", x[i], ch[i], 3, 1, 1);
+            m.ops.back().sm_share = share[i];
             const int y = B.conv(p + ".conv2", t, ch[i], 3, 1, 1, /*res=*/x[i]);
+            m.ops.back().sm_share = share[i];
             B.release(t, true);
             // the module input of blk 0 may have been produced on another stream /
             // is shared: only tensors created inside this loop are stream-local

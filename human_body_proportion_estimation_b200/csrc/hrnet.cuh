@@ -27,6 +27,7 @@ struct HOp {
     size_t b_off = 0;           // offset (in floats) into the bias blob
     int stream = 0;             // branch stream the op runs on
     int join_before = 0;        // all streams must have finished earlier ops before this op starts
+    float sm_share = 0.f;       // > 0: fraction of the SMs this op's persistent launch may occupy (branches run side by side)
 };
 
 struct UmmaPlan;                // conv_umma.cu: per-op tensor maps + tile shape (per batch size)

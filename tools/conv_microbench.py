@@ -27,12 +27,16 @@ def main():
     eng = Engine(0)
     rng = np.random.default_rng(0)
     rows = []
-    for H, W, Cin, Cout, k, s, up, use_res, share in SHAPES:
+    sel = os.environ.get("HBP_MB_SHAPES")
+    shapes = [SHAPES[int(i)] for i in sel.split(",")] if sel else SHAPES
+    for H, W, Cin, Cout, k, s, up, use_res, share in shapes:
         x = rng.standard_normal((P, H, W, Cin)).astype(np.float16)
         w = (rng.standard_normal((Cout, Cin, k, k)) / np.sqrt(Cin * k * k)).astype(np.float16)
         b = np.zeros(Cout, np.float32)
+        if os.environ.get("HBP_MB_NORES"):
+            use_res = False
         res = rng.standard_normal((P, H // s * up, W // s * up, Cout)).astype(np.float16) if use_res else None
-        _, used, ms = eng.conv2d_nhwc(x, w, b, res, s, up, True, engine, time_iters=50)
+        _, used, ms = eng.conv2d_nhwc(x, w, b, res, s, up, True, engine, time_iters=int(os.environ.get("HBP_MB_ITERS", "50")))
         flop = 2.0 * P * (H // s) * (W // s) * Cin * Cout * k * k
         rows.append(dict(shape=[H, W, Cin, Cout, k, s, up], engine=used, us=ms * 1e3, tflops=flop / ms / 1e9,
                          share_pct=share))

@@ -1,0 +1,8 @@
+#!/bin/bash
+TAG=${1:-r01p}
+mkdir -p gpurun_out
+for cfg in "A=1" "HBP_MB_NORES=1"; do
+  echo "=== cfg: $cfg"
+  env $cfg HBP_MB_ITERS=20 HBP_MB_SHAPES=0,1,2,3,4 HBP_CONV_TRACE=1 timeout 300 python tools/conv_microbench.py 2>&1 | grep -v "^\[taps" | cut -c1-420
+done > gpurun_out/mb_trace_$TAG.log 2>&1
+grep -v "A(3..6) issued -\|A(3..6) issued [0-9]* -" gpurun_out/mb_trace_$TAG.log
