@@ -179,13 +179,6 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
-// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute
-// starts while its stream predecessor is still running; everything that does not touch the
-// predecessor's output (barrier init, TMEM allocation, weight / bias loads) runs ahead of
-// pdl_wait(), which returns once the predecessor grid has completed and flushed.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major, hardware swizzle (SM100 format):
@@ -203,6 +196,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes
     d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;
     return d;
 }
+
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute
+// starts while its stream predecessor is still running; everything that does not touch the
+// predecessor's output (barrier init, TMEM allocation, weight / bias loads) runs ahead of
+// pdl_wait(), which returns once the predecessor grid has completed and flushed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 constexpr int kThreads = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
 
@@ -232,14 +232,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int n0 = t * p.tn, h0 = tile_h * p.th, w0 = tile_w * p.tw;
     const int n_off = blockIdx.y * p.n_tile;
 
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        for (int s = 0; s < p.stages; ++s) {
+    pdl_launch_dependents();             // the next launch of this stream may start its prologue
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            mbar_init(tmem_full_bar, 1);
+        }
+        for (int s = lane; s < p.stages; s += 32) {
             mbar_init(full_bar + 8u * s, 1);
             mbar_init(empty_bar + 8u * s, 1);
         }
-        mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -247,6 +250,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                          // activations / residual below are the previous launch's output
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -424,17 +428,18 @@ constexpr uint32_t kHaloBarBytes = 8u * (kMaxAStages * kMaxChunks + 3 * kMaxASta
 // Each CTA walks tiles blockIdx.x, +gridDim.x, ... (grid <= SM count: no partial wave).
 constexpr int kResPrefetch = 8;   // uint4 (8 halfs) of residual a thread may hold in flight
 
-template <int KSTEPS, int MT>
+template <int KSTEPS, int MT, int KS>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmR, const ConvParams p) {
+    constexpr int HW = KS == 3 ? kHaloW : 8;         // pixels per stacked row of the tile in shared memory (halo columns for 3x3)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     if (p.dbg_flags & 4) return;         // bring-up: empty launch (measures the launch / dependency floor of the graph)
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_tile_bytes = p.n_chunks * p.a_chunk_bytes;
     const uint32_t a_base = smem_base;
     const uint32_t b_base = a_base + p.a_stages * a_tile_bytes;
-    const uint32_t r_base = b_base + p.b_slots * 3u * p.b_stage_bytes;  // residual ring: a_stages x r_chunks x r_chunk_bytes
+    const uint32_t r_base = b_base + p.b_slots * (uint32_t)KS * p.b_stage_bytes;  // residual ring: a_stages x r_chunks x r_chunk_bytes
     const uint32_t r_tile_bytes = p.res_smem ? p.r_chunks * p.r_chunk_bytes : 0u;
     const uint32_t bar_base = r_base + p.a_stages * r_tile_bytes;
     const uint32_t a_full = bar_base;                                   // a_stages x n_chunks
@@ -455,14 +460,17 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
     pdl_launch_dependents();             // the next launch of this stream may start its prologue
 
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        if (p.res_smem) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
-        for (int i = 0; i < p.a_stages * p.n_chunks; ++i) mbar_init(a_full + 8u * i, 1);
-        for (int i = 0; i < p.a_stages; ++i) { mbar_init(a_empty + 8u * i, 1); mbar_init(res_full + 8u * i, 1); mbar_init(res_empty + 8u * i, 4); }
-        for (int i = 0; i < p.b_slots; ++i) { mbar_init(b_full + 8u * i, 1); mbar_init(b_empty + 8u * i, 1); }
-        for (int i = 0; i < kMaxAccBufs; ++i) { mbar_init(acc_full + 8u * i, 1); mbar_init(acc_empty + 8u * i, 4); }
+    if (warp == 0) {
+        // barrier init spread over the lanes of warp 0 (one thread doing ~60 inits is a microsecond of prologue)
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            if (p.res_smem) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+        }
+        for (int i = lane; i < p.a_stages * p.n_chunks; i += 32) mbar_init(a_full + 8u * i, 1);
+        for (int i = lane; i < p.a_stages; i += 32) { mbar_init(a_empty + 8u * i, 1); mbar_init(res_full + 8u * i, 1); mbar_init(res_empty + 8u * i, 4); }
+        for (int i = lane; i < p.b_slots; i += 32) { mbar_init(b_full + 8u * i, 1); mbar_init(b_empty + 8u * i, 1); }
+        for (int i = lane; i < kMaxAccBufs; i += 32) { mbar_init(acc_full + 8u * i, 1); mbar_init(acc_empty + 8u * i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -476,7 +484,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
     const uint32_t acc_stride = (uint32_t)(MT * p.n_tile);              // TMEM columns per accumulator buffer
     const uint32_t b_bytes = (uint32_t)p.n_tile * p.row_bytes;          // one tap; a slot holds three (dy = 0..2 of one dx)
-    const uint32_t b_slot_bytes = 3u * p.b_stage_bytes;
+    const uint32_t b_slot_bytes = (uint32_t)KS * p.b_stage_bytes;
 
     if (warp == 0) {
         // ===== TMA producer (warp-wide control flow, one elected lane issues) =====
@@ -501,7 +509,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 for (int cc = 0; cc < p.n_chunks; ++cc) {
                     const uint32_t bar = a_full + 8u * (sa * p.n_chunks + cc);
                     mbar_expect_tx(bar, p.a_box_bytes);
-                    tma_load_4d(a_base + sa * a_tile_bytes + cc * p.a_chunk_bytes, &tmA, bar, cc * p.chunk, w0 - 1, h0 - 1, n0);
+                    tma_load_4d(a_base + sa * a_tile_bytes + cc * p.a_chunk_bytes, &tmA, bar, cc * p.chunk, w0 - KS / 2, h0 - KS / 2, n0);
                 }
             }
             __syncwarp();
@@ -517,12 +525,12 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             // so that the first tile starts as soon as its first tap has landed
             if (elect_one()) {
                 for (int cc = 0; cc < p.n_chunks; ++cc)
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int i = cc * 3 + dx;
-                        mbar_expect_tx(b_full + 8u * i, 3u * b_bytes);
-                        for (int dy = 0; dy < 3; ++dy)
+                    for (int dx = 0; dx < KS; ++dx) {
+                        const int i = cc * KS + dx;
+                        mbar_expect_tx(b_full + 8u * i, (uint32_t)KS * b_bytes);
+                        for (int dy = 0; dy < KS; ++dy)
                             tma_load_2d(b_base + i * b_slot_bytes + dy * p.b_stage_bytes, &tmB, b_full + 8u * i, cc * p.chunk,
-                                        (dy * 3 + dx) * p.Cout + n_off);
+                                        (dy * KS + dx) * p.Cout + n_off);
                     }
             }
             __syncwarp();
@@ -534,13 +542,13 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int j = 0; j < T; ++j) {
             if (!p.b_resident) {
                 for (int cc = 0; cc < p.n_chunks; ++cc)
-                    for (int dx = 0; dx < 3; ++dx) {
+                    for (int dx = 0; dx < KS; ++dx) {
                         mbar_wait(b_empty + 8u * s, ph ^ 1u);
                         if (elect_one()) {
-                            mbar_expect_tx(b_full + 8u * s, 3u * b_bytes);
-                            for (int dy = 0; dy < 3; ++dy)
+                            mbar_expect_tx(b_full + 8u * s, (uint32_t)KS * b_bytes);
+                            for (int dy = 0; dy < KS; ++dy)
                                 tma_load_2d(b_base + s * b_slot_bytes + dy * p.b_stage_bytes, &tmB, b_full + 8u * s, cc * p.chunk,
-                                            (dy * 3 + dx) * p.Cout + n_off);
+                                            (dy * KS + dx) * p.Cout + n_off);
                         }
                         __syncwarp();
                         if (++s == p.b_slots) { s = 0; ph ^= 1u; }
@@ -578,8 +586,8 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // ===== MMA issuers (warp-wide control flow, one elected lane issues) =====
         const int iss = warp - 1;
         constexpr uint32_t kRow16 = KSTEPS * 2;                                 // one pixel row (chunk halfs) in 16-byte units
-        constexpr uint32_t kMtStep = 16u * kHaloW * kRow16;
-        const uint64_t da0 = make_desc(0, p.row_bytes, kHaloW * p.row_bytes);   // A: 8-row groups 10 rows apart
+        constexpr uint32_t kMtStep = 16u * HW * kRow16;
+        const uint64_t da0 = make_desc(0, p.row_bytes, HW * p.row_bytes);   // A: 8-row groups one stacked row (HW pixels) apart
         const uint64_t db0 = make_desc(0, p.row_bytes);
         const uint32_t bstep = p.b_stage_bytes >> 4;                            // one tap of weights in 16-byte units
         const uint32_t idesc = p.idesc, n_tile = (uint32_t)p.n_tile;
@@ -607,26 +615,26 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     // 9 x KSTEPS x MT MMAs of the chunk are one straight-line block under one election
                     // (every instruction between two MMAs idles the pipe: it queues only ~2 of them)
                     tc_fence_after();
-                    const uint64_t b_c = db0 + ((b_base + (uint32_t)(cc * 3) * b_slot_bytes) >> 4);
+                    const uint64_t b_c = db0 + ((b_base + (uint32_t)(cc * KS) * b_slot_bytes) >> 4);
                     const uint32_t fresh = cc == 0 ? 0u : 1u;
                     if (elect_one()) {
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx)
+                        for (int dx = 0; dx < KS; ++dx)
 #pragma unroll
-                            for (int dy = 0; dy < 3; ++dy)
+                            for (int dy = 0; dy < KS; ++dy)
 #pragma unroll
                                 for (int ks = 0; ks < KSTEPS; ++ks)
 #pragma unroll
                                     for (int mt = 0; mt < MT; ++mt)
-                                        umma_f16(d_base + mt * n_tile, a_c + (uint32_t)((dy * kHaloW + dx) * kRow16 + mt * kMtStep + 2 * ks),
-                                                 b_c + (uint32_t)(dx * 3 + dy) * bstep + 2 * ks, idesc, (dx | dy | ks) ? 1u : fresh);
+                                        umma_f16(d_base + mt * n_tile, a_c + (uint32_t)((dy * HW + dx) * kRow16 + mt * kMtStep + 2 * ks),
+                                                 b_c + (uint32_t)(dx * KS + dy) * bstep + 2 * ks, idesc, (dx | dy | ks) ? 1u : fresh);
                     }
                     __syncwarp();
                     continue;
                 }
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const int slot = p.b_resident ? cc * 3 + dx : s;
+                for (int dx = 0; dx < KS; ++dx) {
+                    const int slot = p.b_resident ? cc * KS + dx : s;
                     if (!p.b_resident) mbar_wait(b_full + 8u * s, ph);
                     else if (j < p.issuers) mbar_wait(b_full + 8u * slot, 0);      // this warp's first tile
                     if (dbg && cc == 0 && dx == 0 && j == 0 && lane == 0) dbg[3] = clock64();
@@ -635,13 +643,13 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     const uint32_t fresh = (cc == 0 && dx == 0) ? 0u : 1u;      // first MMA of a tile overwrites
                     if (elect_one()) {
 #pragma unroll
-                        for (int dy = 0; dy < 3; ++dy) {
+                        for (int dy = 0; dy < KS; ++dy) {
                             const uint64_t bd = b_s + (uint32_t)dy * bstep;
 #pragma unroll
                             for (int ks = 0; ks < KSTEPS; ++ks)
 #pragma unroll
                                 for (int mt = 0; mt < MT; ++mt)
-                                    umma_f16(d_base + mt * n_tile, a_c + (uint32_t)((dy * kHaloW + dx) * kRow16 + mt * kMtStep + 2 * ks),
+                                    umma_f16(d_base + mt * n_tile, a_c + (uint32_t)((dy * HW + dx) * kRow16 + mt * kMtStep + 2 * ks),
                                              bd + 2 * ks, idesc, (dy | ks) ? 1u : fresh);
                         }
                         if (!p.b_resident) umma_commit(b_empty + 8u * s);
@@ -907,6 +915,7 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     const HTensor& ti = m.tensors[op.in];
     const int Ho = ti.h, Wo = ti.w;
     ConvParams& p = pl->prm;
+    const int ksz = op.k, hw = ksz == 3 ? kHaloW : 8;
     const int chunk = op.cin == 32 ? 32 : 64, n_chunks = op.cin / chunk;
     if (n_chunks > kMaxChunks) return HBP_OK;
     const uint32_t row_bytes = chunk * 2;
@@ -926,8 +935,8 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
             for (int h = Ho < 16 * mt ? Ho : 16 * mt; h >= 1; --h) {
                 if (Ho % h) continue;
                 if (n > 1 && h != Ho) continue;                 // stacked images need whole images
-                const int rs = h + 2;
-                if (16 * mt < n * rs - 2) continue;             // every group of the tile inside the M-tiles
+                const int rs = h + ksz - 1;
+                if (16 * mt < n * rs - (ksz - 1)) continue;             // every group of the tile inside the M-tiles
                 if (n * h * 2 < 16 * mt && !(n == 1 && h == Ho)) { break; }   // < 50 % useful rows: only if nothing else
                 const long tiles = (long)((capP + n - 1) / n) * (Ho / h) * tiles_w;
                 for (int c = op.cout < 256 ? op.cout : 256; c >= 32; c -= 16) {
@@ -936,13 +945,16 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
                     const long rounds = (items + sms - 1) / sms;
                     // cycles of one M-tile pass over all taps: max(tensor floor, shared-memory feed)
                     const double per_mma = std::max(c / 2.0, (128.0 * 32 + c * 32.0) / 128.0);
-                    const double mma_cyc = (double)rounds * mt * per_mma * 9 * (op.cin / 16);
+                    const double mma_cyc = (double)rounds * mt * per_mma * ksz * ksz * (op.cin / 16);
                     // weight bytes one CTA pulls from L2 (~24 B/clk/SM when every SM streams): once when
                     // they can stay resident, once per tile otherwise
-                    const double w_bytes = 9.0 * op.cin * c * 2;
-                    const bool fits = w_bytes + 2.0 * (16 * mt + 2) * kHaloW * op.cin * 2 < 190e3;
+                    const double w_bytes = (double)ksz * ksz * op.cin * c * 2;
+                    const double a_bytes = (double)(16 * mt + ksz - 1) * hw * op.cin * 2;      // one tile's input box
+                    const bool fits = w_bytes + 2.0 * a_bytes < 190e3;
                     const double w_cyc = (fits ? 1.0 : (double)rounds) * w_bytes / 24.0;
-                    const double cost = std::max(mma_cyc, w_cyc);
+                    // the tile's input box is fetched once per output-channel split: it bounds the 1x1 layers
+                    const double a_cyc = (double)rounds * a_bytes / 24.0;
+                    const double cost = std::max(std::max(mma_cyc, w_cyc), a_cyc);
                     const bool better = cost < best.cost * 0.97 ||
                                         (cost < best.cost * 1.03 && (c > best.n_tile || (c == best.n_tile && mt > best.m)));
                     if (better) best = Cand{n, h, mt, c, items, cost};
@@ -960,13 +972,13 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     }
     if (env_int("HBP_HALO_N", 0) && op.cout % env_int("HBP_HALO_N", 0) == 0) n_tile = env_int("HBP_HALO_N", 0);
     const int tiles_h = Ho / th;
-    const int rs = th + 2;
+    const int rs = th + ksz - 1;
     const long tiles = (long)((capP + tn - 1) / tn) * tiles_h * tiles_w;
     const int n_splits = op.cout / n_tile;
     const long per_cta = (tiles * n_splits + sms - 1) / sms;            // tiles one CTA walks
 
-    const uint32_t a_box_bytes = (uint32_t)(kHaloW * rs * tn) * row_bytes;
-    uint32_t a_chunk_bytes = (uint32_t)((16 * m_tiles + 2) * kHaloW) * row_bytes;
+    const uint32_t a_box_bytes = (uint32_t)(hw * rs * tn) * row_bytes;
+    uint32_t a_chunk_bytes = (uint32_t)((16 * m_tiles + ksz - 1) * hw) * row_bytes;
     if (a_chunk_bytes < a_box_bytes) a_chunk_bytes = a_box_bytes;
     a_chunk_bytes = (a_chunk_bytes + 1023u) & ~1023u;
     const uint32_t b_stage = ((uint32_t)n_tile * row_bytes + 1023u) & ~1023u;
@@ -980,8 +992,8 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     const uint32_t r_chunk_bytes = (r_box_bytes + 1023u) & ~1023u;
     const uint32_t a_tile = a_chunk_bytes * n_chunks + (res_smem ? r_chunks * r_chunk_bytes : 0u);     // one ring stage: halo tile + residual tile
     const uint32_t fixed = kHaloBarBytes + (uint32_t)n_tile * 4 + 1024 + 64;
-    const int k_slots = 3 * n_chunks;                                   // weight slots per tile: (chunk, dx), three taps each
-    const uint32_t b_slot = 3u * b_stage;
+    const int k_slots = ksz * n_chunks;                                 // weight slots per tile: (chunk, dx), ksz taps each
+    const uint32_t b_slot = (uint32_t)ksz * b_stage;
     const uint32_t b_all = (uint32_t)k_slots * b_slot;
     int want_a = (int)std::min<long>(per_cta, env_int("HBP_HALO_ASTAGES", 4));
     if (want_a < 1) want_a = 1;
@@ -1006,11 +1018,11 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     int acc_bufs = 4 * m_tiles * n_tile <= 512 ? 4 : (2 * m_tiles * n_tile <= 512 ? 2 : 1);
     if (env_int("HBP_HALO_BUFS", 0)) acc_bufs = env_int("HBP_HALO_BUFS", 0);
     if (acc_bufs * m_tiles * n_tile > 512) return HBP_OK;
-    if (kHaloW > 256 || rs > 256 || tn > 256) return HBP_OK;
+    if (rs > 256 || tn > 256) return HBP_OK;
 
     p.Ho = Ho; p.Wo = Wo; p.Cout = op.cout; p.up = 1; p.relu = op.relu;
     p.tn = tn; p.th = th; p.tw = 8; p.m_tiles = m_tiles; p.n_tile = n_tile;
-    p.chunk = chunk; p.n_chunks = n_chunks; p.ksz = 3; p.stride = 1;
+    p.chunk = chunk; p.n_chunks = n_chunks; p.ksz = ksz; p.stride = 1;
     p.tiles_w = tiles_w; p.tiles_h = tiles_h;
     p.row_bytes = row_bytes;
     p.a_stage_bytes = 0; p.b_stage_bytes = b_stage; p.tx_bytes = 0;
@@ -1045,14 +1057,14 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     cuuint64_t gdim[4] = {(cuuint64_t)ti.c, (cuuint64_t)ti.w, (cuuint64_t)ti.h, (cuuint64_t)capP};
     cuuint64_t gstr[3] = {(cuuint64_t)ti.c * 2, (cuuint64_t)ti.w * ti.c * 2, (cuuint64_t)ti.h * ti.w * ti.c * 2};
-    cuuint32_t box[4] = {(cuuint32_t)chunk, (cuuint32_t)kHaloW, (cuuint32_t)rs, (cuuint32_t)tn};
+    cuuint32_t box[4] = {(cuuint32_t)chunk, (cuuint32_t)hw, (cuuint32_t)rs, (cuuint32_t)tn};
     cuuint32_t est[4] = {1, 1, 1, 1};
     CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, m.bufs[ti.buf], gdim, gstr, box, est,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         hbp_set_error("cuTensorMapEncodeTiled(A halo) failed (%d) for %s box=(%d,%d,%d,%d)", (int)r, op.name.c_str(),
-                      chunk, kHaloW, rs, tn);
+                      chunk, hw, rs, tn);
         return HBP_ERR_CUDA;
     }
     pl->tmR = pl->tmA;                       // placeholder when the residual does not go through shared memory
@@ -1086,13 +1098,17 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     if (!enc) { delete pl; hbp_set_error("cuTensorMapEncodeTiled unavailable"); return HBP_ERR_CUDA; }
     if (!(ctx->attr_flags & ATTR_UMMA)) {
         HBP_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<2, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<4, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         ctx->attr_flags |= ATTR_UMMA;
     }
-    if (op.k == 3 && op.stride == 1 && op.up == 1 && halo_mode_enabled()) {
+    if ((op.k == 3 || (op.k == 1 && env_int("HBP_HALO_1X1", 1))) && op.stride == 1 && op.up == 1 && halo_mode_enabled()) {
         bool ok = false;
         int st = plan_halo(ctx, m, op, capP, pl, &ok);
         if (st) { delete pl; return st; }
@@ -1187,10 +1203,10 @@ static void launch_halo(dim3 grid, size_t smem, cudaStream_t st, const UmmaPlan*
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
     const int ks = p.chunk / 16;
-    if (ks == 2 && p.m_tiles == 1) cudaLaunchKernelEx(&cfg, conv_umma_halo_kernel<2, 1>, pl->tmA, pl->tmB, pl->tmR, p);
-    else if (ks == 2) cudaLaunchKernelEx(&cfg, conv_umma_halo_kernel<2, 2>, pl->tmA, pl->tmB, pl->tmR, p);
-    else if (p.m_tiles == 1) cudaLaunchKernelEx(&cfg, conv_umma_halo_kernel<4, 1>, pl->tmA, pl->tmB, pl->tmR, p);
-    else cudaLaunchKernelEx(&cfg, conv_umma_halo_kernel<4, 2>, pl->tmA, pl->tmB, pl->tmR, p);
+#define HBP_HALO_CASE(K, M, S) if (ks == K && p.m_tiles == M && p.ksz == S) { cudaLaunchKernelEx(&cfg, conv_umma_halo_kernel<K, M, S>, pl->tmA, pl->tmB, pl->tmR, p); return; }
+    HBP_HALO_CASE(2, 1, 3) HBP_HALO_CASE(2, 2, 3) HBP_HALO_CASE(4, 1, 3) HBP_HALO_CASE(4, 2, 3)
+    HBP_HALO_CASE(2, 1, 1) HBP_HALO_CASE(2, 2, 1) HBP_HALO_CASE(4, 1, 1) HBP_HALO_CASE(4, 2, 1)
+#undef HBP_HALO_CASE
 }
 
 int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, cudaStream_t st) {
@@ -1244,7 +1260,16 @@ int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, 
         }
     }
     if (p.mode == 1) launch_halo(grid, pl->smem_bytes, st, pl, p);
-    else conv_umma_kernel<<<grid, kThreads, pl->smem_bytes, st>>>(pl->tmA, pl->tmB, p);
+    else {
+        static const int pdl = env_int("HBP_PDL", 1);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = pl->smem_bytes; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, conv_umma_kernel, pl->tmA, pl->tmB, p);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return hbp_cuda_fail(e, "conv_umma_kernel", __FILE__, __LINE__);
     return HBP_OK;

@@ -264,22 +264,30 @@ void hrnet_build_program(HrnetModel& m) {
 // ===========================================================================
 namespace {
 
-// conv1: NCHW fp16 (P,3,H,W) -> NHWC fp16 (P,H/2,W/2,64), 3x3 stride 2 pad 1, +bias, ReLU
+// conv1: NCHW fp16 (P,3,H,W) -> NHWC fp16 (P,H/2,W/2,64), 3x3 stride 2 pad 1, +bias, ReLU.
+// One thread per output pixel, all 64 output channels in registers; the 27 x 64 weights sit in
+// shared memory as [tap*3+ci][co] and are read as broadcast float4 (one LDS.128 per 4 FMAs: the
+// scalar-LDS version was shared-memory-issue bound).  100 MB written at batch 64: HBM-bound floor ~18 us.
 __global__ void __launch_bounds__(128)
 stem1_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const float* __restrict__ bias,
              __half* __restrict__ out, int P, int H, int W) {
-    __shared__ float s_w[64 * 27];      // [co][tap*3 + ci]
-    __shared__ float s_b[64];
+    __shared__ __align__(16) float s_w[27 * 64];      // [tap*3 + ci][co]
+    __shared__ __align__(16) float s_b[64];
     for (int i = threadIdx.x; i < 64 * 27; i += blockDim.x) {
-        const int co = i / 27, r = i % 27, tap = r / 3, ci = r % 3;
+        const int r = i / 64, co = i % 64, tap = r / 3, ci = r % 3;
         s_w[i] = __half2float(w[((size_t)tap * 64 + co) * 3 + ci]);      // blob layout [tap][co][ci]
     }
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_b[i] = bias[i];
     __syncthreads();
+    // a warp's 32 pixels are 4 KB of contiguous output: staged in shared memory (XOR-swizzled 16-byte
+    // chunks) and written back as fully coalesced 512-byte rows instead of 32 scattered 16-byte pieces
+    __shared__ __align__(16) uint4 s_out[4][32 * 8];
     const int Ho = H / 2, Wo = W / 2;
     const size_t total = (size_t)P * Ho * Wo;
-    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= total) return;
+    const size_t pix_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = pix_raw < total;
+    const size_t pix = live ? pix_raw : total - 1;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((size_t)Wo * Ho));
     float v[27];
 #pragma unroll
@@ -290,20 +298,39 @@ stem1_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const 
             const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci)
-                v[(dy * 3 + dx) * 3 + ci] = ok ? __half2float(in[(((size_t)n * 3 + ci) * H + hi) * W + wi]) : 0.f;
+                v[(dy * 3 + dx) * 3 + ci] = ok ? __half2float(__ldg(in + (((size_t)n * 3 + ci) * H + hi) * W + wi)) : 0.f;
         }
-    __half* o = out + pix * 64;
-    for (int g = 0; g < 8; ++g) {
-        __align__(16) __half r[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float* ww = s_w + (g * 8 + c) * 27;
-            float acc = s_b[g * 8 + c];
+    for (int g = 0; g < 4; ++g) {                      // 16 output channels at a time
+        float acc[16];
 #pragma unroll
-            for (int t = 0; t < 27; ++t) acc = fmaf(v[t], ww[t], acc);
-            r[c] = __float2half_rn(fmaxf(acc, 0.f));
+        for (int q = 0; q < 4; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_b + g * 16 + 4 * q);
+            acc[4 * q] = b4.x; acc[4 * q + 1] = b4.y; acc[4 * q + 2] = b4.z; acc[4 * q + 3] = b4.w;
         }
-        *reinterpret_cast<uint4*>(o + g * 8) = *reinterpret_cast<const uint4*>(r);
+#pragma unroll
+        for (int t = 0; t < 27; ++t) {
+            const float4* ww = reinterpret_cast<const float4*>(s_w + t * 64 + g * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 w4 = ww[q];
+                acc[4 * q] = fmaf(v[t], w4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v[t], w4.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(v[t], w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v[t], w4.w, acc[4 * q + 3]);
+            }
+        }
+        __align__(16) __half2 r[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) r[c] = __floats2half2_rn(fmaxf(acc[2 * c], 0.f), fmaxf(acc[2 * c + 1], 0.f));
+        s_out[wrp][lane * 8 + ((2 * g) ^ (lane & 7))] = *reinterpret_cast<const uint4*>(&r[0]);
+        s_out[wrp][lane * 8 + ((2 * g + 1) ^ (lane & 7))] = *reinterpret_cast<const uint4*>(&r[4]);
+    }
+    __syncwarp();
+    const size_t warp_pix0 = (size_t)blockIdx.x * blockDim.x + wrp * 32;
+    uint4* o = reinterpret_cast<uint4*>(out + warp_pix0 * 64);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = k * 32 + lane, pl = i >> 3, c = i & 7;
+        if (warp_pix0 + pl < total) o[i] = s_out[wrp][pl * 8 + (c ^ (pl & 7))];
     }
 }
 
@@ -344,42 +371,56 @@ head_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const f
     }
 }
 
-// out = act(res + up(a) [+ up2(b)] [+ up3(c)]), NHWC fp16, nearest upsample; 16 bytes per thread
+// out = act(res + up(a) [+ up2(b)] [+ up3(c)]), NHWC fp16, nearest upsample.  HBM-bound: every thread
+// handles two 16-byte items half the tensor apart, all their loads issued before the first use.
 __global__ void __launch_bounds__(256)
 upsample_add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, const __half* __restrict__ c,
                     const __half* res, __half* out, int P, int H, int W, int C, int fa, int fb, int fc, int relu) {
     const int c8n = C >> 3;
     const size_t total = (size_t)P * H * W * c8n;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int c8 = (int)(i % c8n);
-    const size_t pix = i / c8n;
-    const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
-    float acc[8];
-    {
-        const uint4 q = *reinterpret_cast<const uint4*>(res + pix * C + c8 * 8);
-        const __half2* hq = reinterpret_cast<const __half2*>(&q);
+    const size_t half_n = (total + 1) >> 1;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= half_n) return;
+    size_t idx[2] = {i0, i0 + half_n};
+    uint4 q[2][4];
+    bool on[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hq[k]); acc[2 * k] = f.x; acc[2 * k + 1] = f.y; }
+    for (int u = 0; u < 2; ++u) {
+        on[u] = idx[u] < total;
+        if (!on[u]) continue;
+        const int c8 = (int)(idx[u] % c8n);
+        const size_t pix = idx[u] / c8n;
+        const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
+        auto src = [&](const __half* s, int f) {
+            const int hs = H / f, ws = W / f;
+            return __ldg(reinterpret_cast<const uint4*>(s + (((size_t)n * hs + h / f) * ws + w / f) * C + c8 * 8));
+        };
+        q[u][0] = *reinterpret_cast<const uint4*>(res + pix * C + c8 * 8);
+        q[u][1] = src(a, fa);
+        if (b) q[u][2] = src(b, fb);
+        if (c) q[u][3] = src(c, fc);
     }
-    auto add = [&](const __half* src, int f) {
-        const int hs = H / f, ws = W / f;
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)n * hs + h / f) * ws + w / f) * C + c8 * 8));
-        const __half2* hq = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { const float2 t = __half22float2(hq[k]); acc[2 * k] += t.x; acc[2 * k + 1] += t.y; }
-    };
-    add(a, fa);
-    if (b) add(b, fb);
-    if (c) add(c, fc);
-    __align__(16) __half2 pk[4];
+    for (int u = 0; u < 2; ++u) {
+        if (!on[u]) continue;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        auto add = [&](const uint4& v) {
+            const __half2* hq = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float x0 = acc[2 * k], x1 = acc[2 * k + 1];
-        if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-        pk[k] = __floats2half2_rn(x0, x1);
+            for (int k = 0; k < 4; ++k) { const float2 t = __half22float2(hq[k]); acc[2 * k] += t.x; acc[2 * k + 1] += t.y; }
+        };
+        add(q[u][0]); add(q[u][1]);
+        if (b) add(q[u][2]);
+        if (c) add(q[u][3]);
+        __align__(16) __half2 pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float x0 = acc[2 * k], x1 = acc[2 * k + 1];
+            if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+            pk[k] = __floats2half2_rn(x0, x1);
+        }
+        *reinterpret_cast<uint4*>(out + idx[u] * 8) = *reinterpret_cast<const uint4*>(pk);
     }
-    *reinterpret_cast<uint4*>(out + pix * C + c8 * 8) = *reinterpret_cast<const uint4*>(pk);
 }
 
 // Generic fused conv, NHWC fp16, weights [tap][cout][cin], fp32 accumulate.
@@ -558,7 +599,10 @@ static int ensure_batch(hbp_ctx* ctx, HrnetModel* m, int P) {
     return HBP_OK;
 }
 
-static cudaStream_t stream_of(hbp_ctx* ctx, HrnetModel* m, int s) { return s == 0 ? ctx->stream : m->side[s - 1]; }
+static cudaStream_t stream_of(hbp_ctx* ctx, HrnetModel* m, int s) {
+    static const bool one = getenv("HBP_ONE_STREAM") != nullptr;      // bring-up: serialise the branches on the origin stream
+    return (s == 0 || one) ? ctx->stream : m->side[s - 1];
+}
 
 // all four streams wait for each other (also used to fork at the start / join at the end)
 static int join_all(hbp_ctx* ctx, HrnetModel* m) {
@@ -577,10 +621,21 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
     HBP_CUDA(cudaEventRecord(m->ev_fork, ctx->stream));
     for (int s = 1; s < 4; ++s) HBP_CUDA(cudaStreamWaitEvent(stream_of(ctx, m, s), m->ev_fork, 0));
     uint64_t launches = 0;
+    // bring-up: HBP_OP_TIMING=1 (with HBP_NO_GRAPH=1 HBP_ONE_STREAM=1) prints the device time of every op
+    static const bool op_timing = getenv("HBP_OP_TIMING") != nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(ctx->stream, &cap);
+    const bool timing = op_timing && cap == cudaStreamCaptureStatusNone;
+    std::vector<cudaEvent_t> tev;
+    if (timing) {
+        tev.resize(2 * m->ops.size());
+        for (auto& e : tev) cudaEventCreate(&e);
+    }
     for (size_t i = 0; i < m->ops.size(); ++i) {
         const HOp& op = m->ops[i];
         if (op.join_before) { int s = join_all(ctx, m); if (s) return s; }
         cudaStream_t st = stream_of(ctx, m, op.stream);
+        if (timing) cudaEventRecord(tev[2 * i], st);
         if (op.kind == OP_STEM1) {
             const HTensor& to = m->tensors[op.out];
             const size_t total = (size_t)P * to.h * to.w;
@@ -598,7 +653,7 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
                     m->bufs[ti.buf], m->d_weights + op.w_off, m->d_bias + op.b_off, (float*)heatmaps, P, ti.h * ti.w, ti.c);
         } else if (op.kind == OP_UPADD) {
             const HTensor& to = m->tensors[op.out];
-            const size_t total = (size_t)P * to.h * to.w * (to.c / 8);
+            const size_t total = ((size_t)P * to.h * to.w * (to.c / 8) + 1) / 2;      // two items per thread
             upsample_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
                 m->bufs[m->tensors[op.in].buf], op.in2 >= 0 ? m->bufs[m->tensors[op.in2].buf] : nullptr,
                 op.in3 >= 0 ? m->bufs[m->tensors[op.in3].buf] : nullptr, m->bufs[m->tensors[op.res].buf],
@@ -626,8 +681,20 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
             }
         }
         ++launches;
+        if (timing) cudaEventRecord(tev[2 * i + 1], st);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return hbp_cuda_fail(e, op.name.c_str(), __FILE__, __LINE__);
+    }
+    if (timing) {
+        cudaDeviceSynchronize();
+        for (size_t i = 0; i < m->ops.size(); ++i) {
+            const HOp& op = m->ops[i];
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, tev[2 * i], tev[2 * i + 1]);
+            fprintf(stderr, "[op] %-40s kind=%d cin=%d cout=%d k=%d s=%d stream=%d %8.2f us\n", op.name.c_str(), op.kind, op.cin, op.cout,
+                    op.k, op.stride, op.stream, ms * 1e3f);
+        }
+        for (auto& e : tev) cudaEventDestroy(e);
     }
     // final join back into the origin stream
     for (int s = 1; s < 4; ++s) {
