@@ -186,6 +186,85 @@ def config_dict():
 
 
 # --------------------------------------------------------------------------
+# memory-bound stages on batched launches (at the config shapes K1/K4/K6 move a
+# few MB per call = microseconds of HBM time, below launch latency; their roofline fraction is
+# measured on launches sized to hundreds of MB, algorithmic bytes / CUDA-event time / measured HBM peak)
+# --------------------------------------------------------------------------
+def stage_rooflines(eng, hbm_gbs):
+    import ctypes as C
+    from human_body_proportion_estimation_b200 import geometry, synth
+    from human_body_proportion_estimation_b200._capi import DEVICE, F16, NCHW, NHWC, PRE_COPY, PRE_LETTERBOX, U8, check
+    from human_body_proportion_estimation_b200.engine import KEYPOINT_THRES_LIST
+    lib, ctx = eng._lib, eng._ctx
+    out = {}
+
+    def timed(fn, reps=5):
+        fn(); fn(); eng.sync()
+        ms = []
+        for _ in range(reps):
+            eng.flush_l2()
+            eng.timer_start(3)
+            fn()
+            eng.timer_stop(3)
+            ms.append(eng.timer_ms(3))
+        return min(ms)
+
+    def entry(name, nbytes, ms, note):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"bound": "hbm", "algorithmic_bytes": int(nbytes), "ms": ms, "achieved": gbs, "peak": hbm_gbs,
+                     "unit": "GB/s", "frac": gbs / hbm_gbs, "launch": note}
+
+    # K1: 64 4K frames u8 NHWC -> BGR->RGB copy (A1) and letterbox 640x640 f16 NCHW (A2)
+    nf, fh, fw = 64, 2160, 3840
+    frame = synth.frame_u8(fh, fw, seed=synth.SEED_BASE + 5, smooth=False)
+    d_frames = eng.dev_alloc(nf * frame.nbytes)
+    for i in range(nf):
+        eng.h2d(d_frames + i * frame.nbytes, frame)
+    d_copy = eng.dev_alloc(nf * frame.nbytes)
+    d_lb = eng.dev_alloc(nf * 3 * 640 * 640 * 2)
+    ms = timed(lambda: check(lib.hbp_preprocess(ctx, C.c_void_p(d_frames), nf, fh, fw, PRE_COPY, fh, fw, 1, 128,
+                                                C.c_void_p(d_copy), U8, NHWC, DEVICE)))
+    entry("k1_bgr2rgb_copy_64x4k_u8", 2 * nf * frame.nbytes, ms, "64 frames 2160x3840x3 u8, one launch")
+    ms = timed(lambda: check(lib.hbp_preprocess(ctx, C.c_void_p(d_frames), nf, fh, fw, PRE_LETTERBOX, 640, 640, 1, 128,
+                                                C.c_void_p(d_lb), F16, NCHW, DEVICE)))
+    entry("k1_letterbox_64x4k_to_640_f16", nf * (frame.nbytes + 3 * 640 * 640 * 2), ms,
+          "64 frames 2160x3840x3 u8 -> 3x640x640 f16, one launch (bytes = whole frame + output)")
+    eng.dev_free(d_copy); eng.dev_free(d_lb)
+
+    # K4: 4096 crops (64 per frame) from the 64 4K frames -> (4096,3,256,192) f16
+    P = 4096
+    boxes = synth.person_boxes_yxyx_px(P, fh, fw, seed=synth.SEED_BASE + 6, hmin=300, hmax=1400)
+    mats = geometry.crop_and_resize_matrices(boxes / np.array([fh, fw, fh, fw], np.float32), fh, fw, IN_H, IN_W)
+    fidx = (np.arange(P) // 64).astype(np.int32)
+    d_m = eng.to_device(mats.reshape(P, 6)); d_fi = eng.to_device(fidx)
+    d_cr = eng.dev_alloc(P * 3 * IN_H * IN_W * 2)
+    ms = timed(lambda: check(lib.hbp_crop_warp(ctx, C.c_void_p(d_frames), nf, fh, fw, C.c_void_p(d_m), C.c_void_p(d_fi),
+                                               P, IN_H, IN_W, 1, C.c_void_p(d_cr), F16, DEVICE)))
+    bw = np.clip(boxes[:, 3] - boxes[:, 1], 1, None); bh = np.clip(boxes[:, 2] - boxes[:, 0], 1, None)
+    src = float(np.minimum(bw * bh, 4.0 * IN_H * IN_W).sum()) * 3          # min(box area, 4 taps per output pixel) x 3 B
+    entry("k4_crop_4096x256x192_f16", src + P * 3 * IN_H * IN_W * 2, ms, "4096 crops from 64 4K frames, one launch")
+    eng.dev_free(d_frames); eng.dev_free(d_m); eng.dev_free(d_fi); eng.dev_free(d_cr)
+
+    # K6: decode + proportions on 8192 crops of (17,64,48) f16
+    P = 8192
+    hm = synth.heatmaps(64, dtype=np.float16)
+    d_hm = eng.dev_alloc(P * hm[0].nbytes)
+    for i in range(P // 64):
+        eng.h2d(d_hm + i * hm.nbytes, hm)
+    bx = synth.person_boxes_yxyx_px(P, 1080, 1920, seed=synth.SEED_BASE + 7)
+    d_bx = eng.to_device(bx); d_h = eng.to_device(np.full(P, 175.0)); d_t = eng.to_device(np.asarray(KEYPOINT_THRES_LIST, np.float32))
+    d_kp = eng.dev_alloc(P * 17 * 8); d_sc = eng.dev_alloc(P * 17 * 4); d_ig = eng.dev_alloc(P * 4)
+    d_ln = eng.dev_alloc(P * 44); d_to = eng.dev_alloc(P * 8)
+    ms = timed(lambda: check(lib.hbp_decode_proportions(ctx, C.c_void_p(d_hm), F16, P, 17, 64, 48, C.c_void_p(d_bx), C.c_void_p(d_h),
+                                                        C.c_void_p(d_t), 0, None, C.c_void_p(d_kp), C.c_void_p(d_sc), None,
+                                                        C.c_void_p(d_ig), C.c_void_p(d_ln), C.c_void_p(d_to), DEVICE)))
+    entry("k6_decode_proportions_8192x17x64x48_f16", P * (17 * 64 * 48 * 2 + 17 * 12 + 11 * 4 + 4), ms, "8192 crops, one launch")
+    for d in (d_hm, d_bx, d_h, d_t, d_kp, d_sc, d_ig, d_ln, d_to):
+        eng.dev_free(d)
+    return out
+
+
+# --------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
@@ -325,8 +404,15 @@ def run_ours(args, rank, world, local_rank):
     value = world * P * args.steps / (dev_ms_total * 1e-3)
     e2e_val = world * P * args.steps / e2e_s
 
+    stage_rf = None
+    if world == 1:
+        try:
+            stage_rf = stage_rooflines(eng, pk["hbm"])
+        except Exception as e:
+            stage_rf = {"error": str(e)}
+
     cpu = None
-    if world == 1 or True:
+    if world == 1:          # the CPU baseline is timed on rank 0 at N = 1 only
         try:
             cv, cms, cores, note = cpu_reference_run(8, 2, 1, weights)
             cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port", "sample": note + "; 2 timed steps"}
@@ -349,6 +435,7 @@ def run_ours(args, rank, world, local_rank):
                      "launch_ms_avg": hr_ms / n_conv_launch, "hrnet_ms": hr_ms},
         "cpu_baseline": cpu,
         "stages_ms": stages,
+        "stage_rooflines": stage_rf,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

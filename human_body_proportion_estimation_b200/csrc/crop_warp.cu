@@ -29,7 +29,7 @@ namespace {
 
 constexpr int kBandRows = 8;
 constexpr int kThreads = 256;
-constexpr int kSmemBudget = 64 * 1024;
+constexpr int kSmemBudget = 28 * 1024;    // per CTA: 7 CTAs of 256 threads per SM
 
 struct Affine {
     double m00, m01, m02, m10, m11, m12;
@@ -43,6 +43,19 @@ __device__ __forceinline__ void src_coord(const Affine& A, int x, int y, int& X,
     const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(A.m11, (double)y), A.m12), 1024.0)) + 16;
     X = (X0 + ad) >> 5;
     Y = (Y0 + bd) >> 5;
+}
+
+// uint8 -> float without the conversion unit (I2F runs on the quarter-rate XU pipe, the profile's
+// busiest): 2^23 + b is exactly representable, so (float)b == as_float(0x4B000000 | b) - 2^23
+__device__ __forceinline__ float u8_to_float(uint8_t b) { return __uint_as_float(0x4B000000u | (uint32_t)b) - 8388608.0f; }
+// correctly rounded x / 255 without MUFU.RCP: one residual step on the product with the correctly
+// rounded reciprocal (Markstein); bit-identical to __fdiv_rn(x, 255.0f) for the blend's value range
+// (checked against it by tests/test_gpu_parity.py through the cv2-exact oracle)
+__device__ __forceinline__ float div255(float x) {
+    const float y = 1.0f / 255.0f;
+    const float q = __fmul_rn(x, y);
+    const float r = __fmaf_rn(-q, 255.0f, x);
+    return __fmaf_rn(r, y, q);
 }
 
 template <typename OutT>
@@ -71,9 +84,14 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
     f = f < 0 ? 0 : (f >= n_frames ? n_frames - 1 : f);
     const uint8_t* __restrict__ src = frames + (size_t)f * H * W * 3;
 
-    if (threadIdx.x == 0) {
+    // The band is processed in passes of `rp` output rows (8, 4, 2 or 1): the largest whose source
+    // box fits the shared-memory budget.  A small budget keeps many CTAs resident per SM (the
+    // kernel is latency-bound: box -> stage -> sample are dependent phases), and big boxes
+    // (4K frames, persons filling the frame) no longer fall back to sampling global memory.
+    __shared__ int s_rp;
+    auto box_of = [&](int r0, int nr, int* box, long long* need) {
         int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
-        const int cx[2] = {0, out_w - 1}, cy[2] = {row0, row0 + rows - 1};
+        const int cx[2] = {0, out_w - 1}, cy[2] = {r0, r0 + nr - 1};
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -87,9 +105,32 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
         xmin = max(xmin, 0); ymin = max(ymin, 0);
         xmax = min(xmax, W - 1); ymax = min(ymax, H - 1);
         const int cols = xmax - xmin + 1, nrows = ymax - ymin + 1;
-        s_box[0] = xmin; s_box[1] = ymin; s_box[2] = cols; s_box[3] = nrows;
-        long long need = (cols > 0 && nrows > 0) ? (long long)nrows * (((long long)cols * 3 + 15 + 15) / 16 * 16) : 0;
-        s_use_smem = (cols > 0 && nrows > 0 && need <= kSmemBudget) ? 1 : 0;
+        box[0] = xmin; box[1] = ymin; box[2] = cols; box[3] = nrows;
+        *need = (cols > 0 && nrows > 0) ? (long long)nrows * (((long long)cols * 3 + 15 + 15) / 16 * 16) : 0;
+    };
+    if (threadIdx.x == 0) {
+        int rp = kBandRows;
+        for (; rp > 1; rp >>= 1) {
+            int box[4];
+            long long need;
+            box_of(row0, min(rp, rows), box, &need);
+            if (need <= kSmemBudget) break;
+        }
+        s_rp = rp;
+    }
+    __syncthreads();
+    const int rp = s_rp;
+    const int groups = (out_w + 7) / 8;                 // 8 output pixels per thread-iteration
+    const size_t plane = (size_t)out_h * out_w;
+    OutT* __restrict__ obase = out + (size_t)p * 3 * plane;
+    for (int pr0 = row0; pr0 < row0 + rows; pr0 += rp) {
+    const int prow = min(rp, row0 + rows - pr0);
+    if (threadIdx.x == 0) {
+        int box[4];
+        long long need;
+        box_of(pr0, prow, box, &need);
+        s_box[0] = box[0]; s_box[1] = box[1]; s_box[2] = box[2]; s_box[3] = box[3];
+        s_use_smem = (box[2] > 0 && box[3] > 0 && need <= kSmemBudget) ? 1 : 0;
     }
     __syncthreads();
     const int bx0 = s_box[0], by0 = s_box[1], bcols = s_box[2], brows = s_box[3];
@@ -103,29 +144,40 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
         // sub-16 phase `ph`; taps index with that phase.
         const int chunks_per_row = pitch / 16;
         const uint8_t* frame_end = frames + (size_t)n_frames * H * W * 3;
-        for (int t = threadIdx.x; t < brows * chunks_per_row; t += kThreads) {
-            const int r = t / chunks_per_row, c = t - r * chunks_per_row;
-            const uint8_t* g0 = src + ((size_t)(by0 + r) * W + bx0) * 3;
-            const uint8_t* ga = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(g0) & ~uintptr_t(15)) + 16 * c;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (ga >= frames && ga + 16 <= frame_end) {
-                v = __ldg(reinterpret_cast<const uint4*>(ga));
-            } else {                                    // first/last bytes of the allocation
-                uint8_t* vb = reinterpret_cast<uint8_t*>(&v);
-                for (int k = 0; k < 16; ++k)
-                    if (ga + k >= frames && ga + k < frame_end) vb[k] = __ldg(ga + k);
+        const int n_chunks = brows * chunks_per_row;
+        // four 16-byte loads in flight per thread before the first shared-memory store: the copy
+        // is latency-bound otherwise (one DRAM round trip per loop iteration)
+        for (int t0 = threadIdx.x; t0 < n_chunks; t0 += 4 * kThreads) {
+            uint4 v[4];
+            int off[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + u * kThreads;
+                v[u] = make_uint4(0, 0, 0, 0);
+                off[u] = -1;
+                if (t >= n_chunks) continue;
+                const int r = t / chunks_per_row, c = t - r * chunks_per_row;
+                const uint8_t* g0 = src + ((size_t)(by0 + r) * W + bx0) * 3;
+                const uint8_t* ga = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(g0) & ~uintptr_t(15)) + 16 * c;
+                off[u] = r * pitch + 16 * c;
+                if (ga >= frames && ga + 16 <= frame_end) {
+                    v[u] = __ldg(reinterpret_cast<const uint4*>(ga));
+                } else {                                    // first/last bytes of the allocation
+                    uint8_t* vb = reinterpret_cast<uint8_t*>(&v[u]);
+                    for (int k = 0; k < 16; ++k)
+                        if (ga + k >= frames && ga + k < frame_end) vb[k] = __ldg(ga + k);
+                }
             }
-            *reinterpret_cast<uint4*>(smem + (size_t)r * pitch + 16 * c) = v;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (off[u] >= 0) *reinterpret_cast<uint4*>(smem + off[u]) = v[u];
         }
         __syncthreads();
     }
 
-    const int groups = (out_w + 7) / 8;                 // 8 output pixels per thread-iteration
-    const size_t plane = (size_t)out_h * out_w;
-    OutT* __restrict__ obase = out + (size_t)p * 3 * plane;
-    for (int t = threadIdx.x; t < rows * groups; t += kThreads) {
+    for (int t = threadIdx.x; t < prow * groups; t += kThreads) {
         const int ry = t / groups, gx = t - ry * groups;
-        const int y = row0 + ry, xbeg = gx * 8;
+        const int y = pr0 + ry, xbeg = gx * 8;
         OutT res[3][8];
         // per-row constants
         const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(A.m01, (double)y), A.m02), 1024.0)) + 16;
@@ -150,19 +202,19 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
                     const uint8_t* g0 = src + ((size_t)yy * W + bx0) * 3;
                     const int ph = (int)(reinterpret_cast<uintptr_t>(g0) & 15);
                     q = smem + (size_t)(yy - by0) * pitch + ph + (xx - bx0) * 3;
-                    acc[0] += (float)q[0] * wgt; acc[1] += (float)q[1] * wgt; acc[2] += (float)q[2] * wgt;
+                    acc[0] += u8_to_float(q[0]) * wgt; acc[1] += u8_to_float(q[1]) * wgt; acc[2] += u8_to_float(q[2]) * wgt;
                 } else {
                     q = src + ((size_t)yy * W + xx) * 3;
-                    acc[0] += (float)__ldg(q) * wgt; acc[1] += (float)__ldg(q + 1) * wgt; acc[2] += (float)__ldg(q + 2) * wgt;
+                    acc[0] += u8_to_float(__ldg(q)) * wgt; acc[1] += u8_to_float(__ldg(q + 1)) * wgt; acc[2] += u8_to_float(__ldg(q + 2)) * wgt;
                 }
             };
             tap(sy, sx, in_y0 && in_x0, w00);
             tap(sy, sx + 1, in_y0 && in_x1, w01);
             tap(sy + 1, sx, in_y1 && in_x0, w10);
             tap(sy + 1, sx + 1, in_y1 && in_x1, w11);
-            res[0][k] = to_out<OutT>(__fdiv_rn(swap_rb ? acc[2] : acc[0], 255.0f));
-            res[1][k] = to_out<OutT>(__fdiv_rn(acc[1], 255.0f));
-            res[2][k] = to_out<OutT>(__fdiv_rn(swap_rb ? acc[0] : acc[2], 255.0f));
+            res[0][k] = to_out<OutT>(div255(swap_rb ? acc[2] : acc[0]));
+            res[1][k] = to_out<OutT>(div255(acc[1]));
+            res[2][k] = to_out<OutT>(div255(swap_rb ? acc[0] : acc[2]));
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -176,6 +228,8 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
                 for (int k = 0; k < 8 && xbeg + k < out_w; ++k) o[k] = res[c][k];
             }
         }
+    }
+    __syncthreads();            // the next pass overwrites the staged rows
     }
 }
 

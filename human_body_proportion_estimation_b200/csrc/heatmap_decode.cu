@@ -22,7 +22,7 @@
 namespace {
 
 constexpr int kMaxJ = 32;
-constexpr int kWarps = 17;
+constexpr int kWarps = 9;        // two joints per warp: small CTAs, seven resident per SM, so one CTA's geometry tail overlaps the others' streaming
 constexpr int kThreads = kWarps * 32;
 
 struct Best {
@@ -101,6 +101,13 @@ __device__ __forceinline__ Best scan_f16(const __half* __restrict__ m, int n, in
             }
         };
         int i = lane;
+        for (; i + 96 < n8; i += 128) {          // 4 independent 16 B loads in flight
+            uint4 a = __ldg(m8 + i), c = __ldg(m8 + i + 32), d = __ldg(m8 + i + 64), e = __ldg(m8 + i + 96);
+            feed8(a, 8 * i);
+            feed8(c, 8 * i + 256);
+            feed8(d, 8 * i + 512);
+            feed8(e, 8 * i + 768);
+        }
         for (; i + 32 < n8; i += 64) {
             uint4 a = __ldg(m8 + i), c = __ldg(m8 + i + 32);
             feed8(a, 8 * i);

@@ -111,17 +111,25 @@ void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const
                   bool multi_scale_output) {
     HrnetModel& m = B.m;
     const int nb = (int)x.size();
-    // The branches run side by side, one stream each.  HBP_BRANCH_SHARE=a,b,c,d gives every branch's
-    // persistent conv launches a fixed share of the SMs so that the launches are resident at once;
-    // measured slower than letting every launch take the whole GPU (profiles/r01_branch_share.log),
-    // so the default (0) is no partition.
-    float share[4] = {0.f, 0.f, 0.f, 0.f};
-    if (const char* e = getenv("HBP_BRANCH_SHARE")) {
-        float v[4] = {0, 0, 0, 0};
-        if (sscanf(e, "%f,%f,%f,%f", &v[0], &v[1], &v[2], &v[3]) >= nb) {
-            float tot = 0;
-            for (int i = 0; i < nb; ++i) tot += v[i];
-            for (int i = 0; i < nb; ++i) share[i] = v[i] / tot;
+    // The branches run side by side, one stream each, and every branch's persistent conv launches take a
+    // fixed share of the SMs (~ its tensor-pipe + epilogue time per layer: equal FLOPs, but narrow N
+    // and partly filled M-tiles cost more): the launches of a level are then resident at once, and
+    // the launch gap / pipeline fill of one overlaps the steady state of the others
+    // (profiles/r01_branch_share.log).  HBP_BRANCH_SHARE<nb>=a,b,.. overrides the table for nb branches.
+    static const float kShare[5][4] = {{}, {1.f}, {0.64f, 0.36f}, {0.44f, 0.20f, 0.36f}, {0.36f, 0.20f, 0.26f, 0.18f}};
+    float share[4] = {kShare[nb][0], kShare[nb][1], kShare[nb][2], kShare[nb][3]};
+    {
+        char key[32];
+        snprintf(key, sizeof(key), "HBP_BRANCH_SHARE%d", nb);
+        const char* e = getenv(key);
+        if (!e) e = getenv("HBP_BRANCH_SHARE");
+        if (e) {
+            float v[4] = {0, 0, 0, 0};
+            if (sscanf(e, "%f,%f,%f,%f", &v[0], &v[1], &v[2], &v[3]) >= nb) {
+                float tot = 0;
+                for (int i = 0; i < nb; ++i) tot += v[i];
+                for (int i = 0; i < nb; ++i) share[i] = tot > 0 ? v[i] / tot : 0.f;
+            }
         }
     }
     for (int i = 0; i < nb; ++i) {
