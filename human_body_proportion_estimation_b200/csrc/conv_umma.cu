@@ -78,6 +78,7 @@ struct ConvParams {
     int teams;                   // halo mode: epilogue teams (2 needs an even number of ring stages and accumulator buffers) (2: alternate tiles, one accumulator buffer each)
     int dbg_flags;               // bring-up experiments: 1 = skip the output stores, 2 = skip the bias loads
     long long* dbg;              // optional phase timestamps (8 per CTA, first 64 CTAs), bring-up only
+    unsigned long long* tl;      // optional [start, end] globaltimer stamps of this launch (HBP_TIMELINE)
 };
 
 struct UmmaPlan {
@@ -201,6 +202,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes
 // starts while its stream predecessor is still running; everything that does not touch the
 // predecessor's output (barrier init, TMEM allocation, weight / bias loads) runs ahead of
 // pdl_wait(), which returns once the predecessor grid has completed and flushed.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -233,6 +239,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int n_off = blockIdx.y * p.n_tile;
 
     pdl_launch_dependents();             // the next launch of this stream may start its prologue
+    if (p.tl && threadIdx.x == 0) atomicMin(p.tl, globaltimer_ns());
     if (warp == 0) {
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -390,6 +397,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
+    if (p.tl && threadIdx.x == 0) atomicMax(p.tl + 1, globaltimer_ns());
 }
 
 
@@ -459,6 +467,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     long long* dbg = (p.dbg && blockIdx.x < 64 && blockIdx.y == 0) ? p.dbg + blockIdx.x * 256 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
     pdl_launch_dependents();             // the next launch of this stream may start its prologue
+    if (p.tl && threadIdx.x == 0) atomicMin(p.tl, globaltimer_ns());
 
     if (warp == 0) {
         // barrier init spread over the lanes of warp 0 (one thread doing ~60 inits is a microsecond of prologue)
@@ -828,6 +837,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         tmem_dealloc(tmem_base, p.tmem_cols);
         if (dbg && lane == 0) dbg[7] = clock64();
     }
+    if (p.tl && threadIdx.x == 0) atomicMax(p.tl + 1, globaltimer_ns());
 }
 
 int halo_mode_enabled() {
@@ -1210,9 +1220,9 @@ static void launch_halo(dim3 grid, size_t smem, cudaStream_t st, const UmmaPlan*
 }
 
 int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, cudaStream_t st) {
-    (void)m; (void)op_index;
     ConvParams p = pl->prm;
     p.P = P;
+    p.tl = m.d_timeline ? m.d_timeline + 2 * op_index : nullptr;
     const int tiles_n = (P + p.tn - 1) / p.tn;
     dim3 grid((unsigned)(tiles_n * p.tiles_h * p.tiles_w), (unsigned)pl->n_splits);
     if (p.mode == 1) {

@@ -524,6 +524,12 @@ conv_simt_kernel(const __half* __restrict__ in, const __half* __restrict__ w, co
 
 }  // namespace
 
+__global__ void timeline_stamp_kernel(unsigned long long* slot, int is_end) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    if (is_end) atomicMax(slot + 1, t); else atomicMin(slot, t);
+}
+
 // ===========================================================================
 // Executor
 // ===========================================================================
@@ -548,6 +554,7 @@ void hrnet_free(hbp_ctx* ctx) {
     HrnetModel* m = ctx->hrnet;
     if (!m) return;
     free_batch_state(ctx, m);
+    if (m->d_timeline) cudaFree(m->d_timeline);
     if (m->d_weights) cudaFree(m->d_weights);
     if (m->d_bias) cudaFree(m->d_bias);
     for (int i = 0; i < 3; ++i) {
@@ -644,6 +651,8 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
         if (op.join_before) { int s = join_all(ctx, m); if (s) return s; }
         cudaStream_t st = stream_of(ctx, m, op.stream);
         if (timing) cudaEventRecord(tev[2 * i], st);
+        const bool stamp = m->d_timeline && op.kind != OP_CONV;      // conv kernels stamp themselves
+        if (stamp) timeline_stamp_kernel<<<1, 1, 0, st>>>(m->d_timeline + 2 * i, 0);
         if (op.kind == OP_STEM1) {
             const HTensor& to = m->tensors[op.out];
             const size_t total = (size_t)P * to.h * to.w;
@@ -689,6 +698,7 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
             }
         }
         ++launches;
+        if (stamp) timeline_stamp_kernel<<<1, 1, 0, st>>>(m->d_timeline + 2 * i, 1);
         if (timing) cudaEventRecord(tev[2 * i + 1], st);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return hbp_cuda_fail(e, op.name.c_str(), __FILE__, __LINE__);
@@ -718,6 +728,31 @@ int hrnet_forward(hbp_ctx* ctx, const __half* crops, int P, void* heatmaps, int 
     if (!m) { hbp_set_error("no model loaded"); return HBP_ERR_STATE; }
     int s = ensure_batch(ctx, m, P);
     if (s) return s;
+    static const bool want_tl = getenv("HBP_TIMELINE") != nullptr;
+    if (want_tl) {
+        const size_t n = m->ops.size();
+        if (!m->d_timeline) HBP_CUDA(cudaMalloc(&m->d_timeline, 2 * n * sizeof(unsigned long long)));
+        if (m->timeline_pending) {
+            // dump the stamps of the previous forward (device ns, relative to its first op)
+            HBP_CUDA(cudaStreamSynchronize(ctx->stream));
+            std::vector<unsigned long long> h(2 * n);
+            HBP_CUDA(cudaMemcpy(h.data(), m->d_timeline, 2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            unsigned long long t0 = ~0ull;
+            for (size_t i = 0; i < n; ++i) if (h[2 * i] < t0) t0 = h[2 * i];
+            for (size_t i = 0; i < n; ++i) {
+                const HOp& op = m->ops[i];
+                if (h[2 * i] == ~0ull) continue;
+                fprintf(stderr, "[tl] %3zu %-40s kind=%d cin=%d cout=%d k=%d s=%d stream=%d start %9.2f end %9.2f us\n", i, op.name.c_str(), op.kind,
+                        op.cin, op.cout, op.k, op.stride, op.stream, (double)(h[2 * i] - t0) * 1e-3, (double)(h[2 * i + 1] - t0) * 1e-3);
+            }
+            fprintf(stderr, "[tl] ----\n");
+        }
+        std::vector<unsigned long long> init(2 * n);
+        for (size_t i = 0; i < n; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0; }
+        HBP_CUDA(cudaMemcpyAsync(m->d_timeline, init.data(), 2 * n * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+        HBP_CUDA(cudaStreamSynchronize(ctx->stream));
+        m->timeline_pending = true;
+    }
     const bool same_key = m->graph_exec && m->graph_P == P && m->graph_dtype == out_dtype &&
                           m->graph_in == (const void*)crops && m->graph_out == heatmaps &&
                           m->graph_engine == m->engine;

@@ -54,6 +54,8 @@ struct HrnetModel {
     cudaStream_t side[3] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
     std::vector<cudaEvent_t> ev_pool;
+    unsigned long long* d_timeline = nullptr;   // HBP_TIMELINE: [start, end] globaltimer ns per op, written by the kernels
+    bool timeline_pending = false;
 };
 
 // builder (hrnet.cu)
