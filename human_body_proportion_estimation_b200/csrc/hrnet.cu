@@ -28,11 +28,15 @@
 // ===========================================================================
 namespace {
 
+constexpr int kStreams = 4;      // more streams were measured slower: every cross-stream edge of the graph costs ~10 us of start latency (profiles/r01_fuse_spread.log)
+
 struct Builder {
     HrnetModel& m;
+    std::vector<int> writer;        // tensor id -> index of the op that wrote it last
+    int last_join_op = 0;           // ops before this index are ordered against everything by a global join
     // free buffers by size: usable by everyone / usable by one stream / waiting for the next join
     std::multimap<size_t, int> free_all;
-    std::multimap<size_t, int> free_stream[4];
+    std::multimap<size_t, int> free_stream[kStreams];
     std::vector<std::pair<size_t, int>> pending;
     int cur_stream = 0;
     bool pending_join = false;
@@ -72,10 +76,23 @@ struct Builder {
         pending_join = true;
         for (auto& p : pending) free_all.insert(p);
         pending.clear();
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < kStreams; ++s) {
             for (auto& p : free_stream[s]) free_all.insert(p);
             free_stream[s].clear();
         }
+        last_join_op = (int)m.ops.size();
+    }
+    // cross-stream read-after-write: the op about to be pushed (on `stream`) reads tensor `tid`
+    void depend(HOp& op, int tid) {
+        if (tid < 0 || tid >= (int)writer.size()) return;
+        const int w = writer[tid];
+        if (w < 0 || w < last_join_op || m.ops[w].stream == op.stream) return;
+        op.wait_ops.push_back(w);
+        m.ops[w].signal = 1;
+    }
+    void wrote(int tid, int op_index) {
+        if ((int)writer.size() <= tid) writer.resize(tid + 1, -1);
+        writer[tid] = op_index;
     }
     int conv(const std::string& name, int in, int cout, int k, int stride, int relu, int res = -1,
              int out = -1, int up = 1) {
@@ -94,8 +111,12 @@ struct Builder {
         m.n_biases += cout;
         op.stream = cur_stream;
         op.join_before = pending_join ? 1 : 0;
+        if (pending_join) last_join_op = (int)m.ops.size();
         pending_join = false;
+        depend(op, in);
+        depend(op, res);
         m.ops.push_back(op);
+        wrote(out, (int)m.ops.size() - 1);
         return out;
     }
 };
@@ -155,7 +176,18 @@ void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const
     B.join();
     const int n_out = multi_scale_output ? nb : 1;
     std::vector<int> y(n_out);
-    for (int i = 0; i < n_out; ++i) {
+    // The terms of a fuse stage are independent strands (a stride-2 chain, a low-resolution 1x1 conv).
+    // HBP_FUSE_SPREAD=1 rotates them over the streams (they meet again through per-op events,
+    // HOp::wait_ops); measured slower than one stream per output -- the extra cross-stream edges cost
+    // more start latency than the shorter chains save (profiles/r01_fuse_spread.log) -- so it is off.
+    static const bool spread = getenv("HBP_FUSE_SPREAD") != nullptr;
+    int rr = 0;
+    auto next_stream = [&](int dflt) { return spread ? (rr++ % kStreams) : dflt; };
+    // outputs in descending order (the longest stride-2 chains are issued first, each on its own
+    // stream); the upsample-adds, which wait for everything, are issued last so that they do not sit
+    // in a stream ahead of an independent strand
+    std::vector<HOp> upadds;
+    for (int i = n_out - 1; i >= 0; --i) {
         B.cur_stream = i;
         const HTensor ti = m.tensors[x[i]];
         y[i] = B.new_tensor(ti.c, ti.h, ti.w);
@@ -163,6 +195,7 @@ void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const
         for (int j = 0; j < i; ++j) {
             const int last = (i == nb - 1) && (j == i - 1);
             int cur = x[j];
+            B.cur_stream = next_stream(i);
             for (int k = 0; k < i - j; ++k) {
                 const std::string nm = pre + S(".fuse_layers.%d.%d.%d.0", i, j, k);
                 if (k == i - j - 1) {
@@ -179,9 +212,11 @@ void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const
         if (i < nb - 1) {
             int lows[3] = {-1, -1, -1}, ups[3] = {1, 1, 1}, nl = 0;
             for (int j = i + 1; j < nb; ++j) {
+                B.cur_stream = next_stream(i);
                 lows[nl] = B.conv(pre + S(".fuse_layers.%d.%d.0", i, j), x[j], ch[i], 1, 1, 0);
                 ups[nl++] = 1 << (j - i);
             }
+            B.cur_stream = i;
             HOp op;
             op.kind = OP_UPADD;
             op.name = pre + S(".fuse_layers.%d.upadd", i);
@@ -191,11 +226,20 @@ void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const
             op.cin = op.cout = ch[i];
             op.relu = 1;
             op.stream = B.cur_stream;
-            op.join_before = B.pending_join ? 1 : 0;
-            B.pending_join = false;
-            m.ops.push_back(op);
-            for (int q = 0; q < nl; ++q) B.release(lows[q], true);
+            upadds.push_back(op);
         }
+    }
+    for (HOp& op : upadds) {
+        B.cur_stream = op.stream;
+        op.join_before = B.pending_join ? 1 : 0;
+        if (B.pending_join) B.last_join_op = (int)m.ops.size();
+        B.pending_join = false;
+        B.depend(op, op.in); B.depend(op, op.in2); B.depend(op, op.in3); B.depend(op, op.res);
+        m.ops.push_back(op);
+        B.wrote(op.out, (int)m.ops.size() - 1);
+        B.release(op.in, true);
+        if (op.in2 >= 0) B.release(op.in2, true);
+        if (op.in3 >= 0) B.release(op.in3, true);
     }
     for (int j = 0; j < nb; ++j) B.release(x[j], false);
     B.join();
@@ -557,12 +601,12 @@ void hrnet_free(hbp_ctx* ctx) {
     if (m->d_timeline) cudaFree(m->d_timeline);
     if (m->d_weights) cudaFree(m->d_weights);
     if (m->d_bias) cudaFree(m->d_bias);
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < kStreams - 1; ++i) {
         if (m->side[i]) cudaStreamDestroy(m->side[i]);
         if (m->ev_join[i]) cudaEventDestroy(m->ev_join[i]);
     }
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
-    for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : m->ev_pool) if (e) cudaEventDestroy(e);
     delete m;
     ctx->hrnet = nullptr;
 }
@@ -584,7 +628,7 @@ int hrnet_load(hbp_ctx* ctx, int width, int in_h, int in_w, const void* w16, siz
     HBP_CUDA(cudaMalloc(&m->d_bias, nb * sizeof(float)));
     HBP_CUDA(cudaMemcpyAsync(m->d_weights, w16, nw * sizeof(__half), cudaMemcpyHostToDevice, ctx->stream));
     HBP_CUDA(cudaMemcpyAsync(m->d_bias, bias, nb * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < kStreams - 1; ++i) {
         HBP_CUDA(cudaStreamCreateWithFlags(&m->side[i], cudaStreamNonBlocking));
         HBP_CUDA(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
     }
@@ -619,14 +663,20 @@ static cudaStream_t stream_of(hbp_ctx* ctx, HrnetModel* m, int s) {
     return (s == 0 || one) ? ctx->stream : m->side[s - 1];
 }
 
-// all four streams wait for each other (also used to fork at the start / join at the end)
+// all streams wait for each other.  Every stream records one event and waits for the events of the
+// others directly: in the captured graph the first kernel after the join then depends on the last
+// kernels before it through ONE edge each (gathering into the origin stream and forking out again put
+// two empty nodes on every path, ~15 us per join on the device timeline).
 static int join_all(hbp_ctx* ctx, HrnetModel* m) {
-    for (int s = 1; s < 4; ++s) {
-        HBP_CUDA(cudaEventRecord(m->ev_join[s - 1], stream_of(ctx, m, s)));
-        HBP_CUDA(cudaStreamWaitEvent(ctx->stream, m->ev_join[s - 1], 0));
-    }
+    static const bool one = getenv("HBP_ONE_STREAM") != nullptr;
+    if (one) return HBP_OK;
     HBP_CUDA(cudaEventRecord(m->ev_fork, ctx->stream));
-    for (int s = 1; s < 4; ++s) HBP_CUDA(cudaStreamWaitEvent(stream_of(ctx, m, s), m->ev_fork, 0));
+    for (int s = 1; s < kStreams; ++s) HBP_CUDA(cudaEventRecord(m->ev_join[s - 1], stream_of(ctx, m, s)));
+    for (int s = 0; s < kStreams; ++s)
+        for (int t = 0; t < kStreams; ++t) {
+            if (t == s) continue;
+            HBP_CUDA(cudaStreamWaitEvent(stream_of(ctx, m, s), t == 0 ? m->ev_fork : m->ev_join[t - 1], 0));
+        }
     return HBP_OK;
 }
 
@@ -634,7 +684,8 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
                      uint64_t* n_launch) {
     // fork: side streams join the origin stream (required for capture)
     HBP_CUDA(cudaEventRecord(m->ev_fork, ctx->stream));
-    for (int s = 1; s < 4; ++s) HBP_CUDA(cudaStreamWaitEvent(stream_of(ctx, m, s), m->ev_fork, 0));
+    for (int s = 1; s < kStreams; ++s) HBP_CUDA(cudaStreamWaitEvent(stream_of(ctx, m, s), m->ev_fork, 0));
+    if (m->ev_pool.size() < m->ops.size()) m->ev_pool.resize(m->ops.size(), nullptr);
     uint64_t launches = 0;
     // bring-up: HBP_OP_TIMING=1 (with HBP_NO_GRAPH=1 HBP_ONE_STREAM=1) prints the device time of every op
     static const bool op_timing = getenv("HBP_OP_TIMING") != nullptr;
@@ -650,6 +701,7 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
         const HOp& op = m->ops[i];
         if (op.join_before) { int s = join_all(ctx, m); if (s) return s; }
         cudaStream_t st = stream_of(ctx, m, op.stream);
+        for (int w : op.wait_ops) HBP_CUDA(cudaStreamWaitEvent(st, m->ev_pool[w], 0));
         if (timing) cudaEventRecord(tev[2 * i], st);
         const bool stamp = m->d_timeline && op.kind != OP_CONV;      // conv kernels stamp themselves
         if (stamp) timeline_stamp_kernel<<<1, 1, 0, st>>>(m->d_timeline + 2 * i, 0);
@@ -698,6 +750,10 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
             }
         }
         ++launches;
+        if (op.signal) {
+            if (!m->ev_pool[i]) HBP_CUDA(cudaEventCreateWithFlags(&m->ev_pool[i], cudaEventDisableTiming));
+            HBP_CUDA(cudaEventRecord(m->ev_pool[i], st));
+        }
         if (stamp) timeline_stamp_kernel<<<1, 1, 0, st>>>(m->d_timeline + 2 * i, 1);
         if (timing) cudaEventRecord(tev[2 * i + 1], st);
         cudaError_t e = cudaGetLastError();
@@ -715,7 +771,7 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
         for (auto& e : tev) cudaEventDestroy(e);
     }
     // final join back into the origin stream
-    for (int s = 1; s < 4; ++s) {
+    for (int s = 1; s < kStreams; ++s) {
         HBP_CUDA(cudaEventRecord(m->ev_join[s - 1], stream_of(ctx, m, s)));
         HBP_CUDA(cudaStreamWaitEvent(ctx->stream, m->ev_join[s - 1], 0));
     }

@@ -28,6 +28,8 @@ struct HOp {
     int stream = 0;             // branch stream the op runs on
     int join_before = 0;        // all streams must have finished earlier ops before this op starts
     float sm_share = 0.f;       // > 0: fraction of the SMs this op's persistent launch may occupy (branches run side by side)
+    std::vector<int> wait_ops;  // ops on OTHER streams that must have finished first (producers of this op's inputs since the last join)
+    int signal = 0;             // some later op waits for this one: record an event after it
 };
 
 struct UmmaPlan;                // conv_umma.cu: per-op tensor maps + tile shape (per batch size)
@@ -51,8 +53,8 @@ struct HrnetModel {
     const void* graph_in = nullptr;
     void* graph_out = nullptr;
     uint64_t graph_nodes = 0;
-    cudaStream_t side[3] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
+    cudaStream_t side[7] = {};                  // streams 1.. (stream 0 is the context's): one per resolution branch
+    cudaEvent_t ev_fork = nullptr, ev_join[7] = {};
     std::vector<cudaEvent_t> ev_pool;
     unsigned long long* d_timeline = nullptr;   // HBP_TIMELINE: [start, end] globaltimer ns per op, written by the kernels
     bool timeline_pending = false;
