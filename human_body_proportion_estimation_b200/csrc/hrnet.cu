@@ -270,7 +270,13 @@ void hrnet_build_program(HrnetModel& m) {
     for (int b = 0; b < 4; ++b) {
         const std::string p = S("layer1.%d", b);
         int res = x;
-        if (b == 0) res = B.conv(p + ".downsample.0", x, 256, 1, 1, 0);
+        if (b == 0) {
+            // the projection shortcut is independent of the 1x1 -> 3x3 chain: it runs beside it on stream 1
+            // and meets conv3 again through an event (HOp::wait_ops)
+            B.cur_stream = 1;
+            res = B.conv(p + ".downsample.0", x, 256, 1, 1, 0);
+            B.cur_stream = 0;
+        }
         const int t1 = B.conv(p + ".conv1", x, 64, 1, 1, 1);
         const int t2 = B.conv(p + ".conv2", t1, 64, 3, 1, 1);
         B.release(t1, true);
@@ -283,8 +289,10 @@ void hrnet_build_program(HrnetModel& m) {
     // transition1
     std::vector<int> xs(2);
     xs[0] = B.conv("transition1.0.0", x, C, 3, 1, 1);
+    B.cur_stream = 1;                  // independent of transition1.0: side by side, on the stream of the branch it feeds
     xs[1] = B.conv("transition1.1.0.0", x, 2 * C, 3, 2, 1);
-    B.release(x, true);
+    B.cur_stream = 0;
+    B.release(x, false);
     B.join();
     std::vector<int> ch = {C, 2 * C};
     stage_module(B, "stage2.0", xs, ch, true);
