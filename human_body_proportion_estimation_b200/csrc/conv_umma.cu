@@ -212,10 +212,10 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 constexpr int kThreads = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
 
-__global__ void __launch_bounds__(kThreads)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const ConvParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
+// One output tile of one convolution (mode 0: one TMA box per tap).  Shared by the single-conv
+// kernel and the grouped kernel below; `bx` / `by` are the tile / output-channel-split indices.
+__device__ __forceinline__ void conv_umma_body(const CUtensorMap* tmAp, const CUtensorMap* tmBp, const ConvParams& p,
+                                               const int bx, const int by, uint8_t* smem_raw) {
     // carve: [A stages][B stages] (1024-aligned), then barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base;
@@ -232,18 +232,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int k_iters = taps * p.n_chunks;
 
     // tile coordinates
-    int t = blockIdx.x;
+    int t = bx;
     const int tile_w = t % p.tiles_w; t /= p.tiles_w;
     const int tile_h = t % p.tiles_h; t /= p.tiles_h;
     const int n0 = t * p.tn, h0 = tile_h * p.th, w0 = tile_w * p.tw;
-    const int n_off = blockIdx.y * p.n_tile;
+    const int n_off = by * p.n_tile;
 
     pdl_launch_dependents();             // the next launch of this stream may start its prologue
     if (p.tl && threadIdx.x == 0) atomicMin(p.tl, globaltimer_ns());
     if (warp == 0) {
         if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(tmAp) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(tmBp) : "memory");
             mbar_init(tmem_full_bar, 1);
         }
         for (int s = lane; s < p.stages; s += 32) {
@@ -253,7 +253,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
-    for (int i = threadIdx.x; i < p.n_tile; i += kThreads) s_bias[i] = p.bias[blockIdx.y * p.n_tile + i];
+    for (int i = threadIdx.x; i < p.n_tile; i += kThreads) s_bias[i] = p.bias[by * p.n_tile + i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -273,9 +273,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(empty_bar + 8u * s, ph ^ 1u);
                 if (elect_one()) {
                     mbar_expect_tx(full_bar + 8u * s, p.tx_bytes);
-                    tma_load_4d(a_base + s * p.a_stage_bytes, &tmA, full_bar + 8u * s,
+                    tma_load_4d(a_base + s * p.a_stage_bytes, tmAp, full_bar + 8u * s,
                                 cc * p.chunk, w0 * p.stride + dx, h0 * p.stride + dy, n0);
-                    tma_load_2d(b_base + s * p.b_stage_bytes, &tmB, full_bar + 8u * s,
+                    tma_load_2d(b_base + s * p.b_stage_bytes, tmBp, full_bar + 8u * s,
                                 cc * p.chunk, tap * p.Cout + n_off);
                 }
                 __syncwarp();
@@ -400,6 +400,276 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.tl && threadIdx.x == 0) atomicMax(p.tl + 1, globaltimer_ns());
 }
 
+
+__global__ void __launch_bounds__(kThreads)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    conv_umma_body(&tmA, &tmB, p, (int)blockIdx.x, (int)blockIdx.y, smem_raw);
+}
+
+// Persistent grouped launch (mode 0: one TMA box per tap).  A group is a list of independent
+// convolutions -- the links of the stride-2 chains and the low-resolution 1x1 convs of one fuse level,
+// or a single stride-2 convolution -- whose (conv, tile, output-channel split) work items form one
+// list that <= one CTA per SM walks with a stride.  A one-tile-per-CTA grid spends ~10 us of
+// TMEM allocation / barrier setup / pipeline fill / drain on ~0.5 us of MMAs; here the prologue is
+// paid once per SM, the TMA ring runs on across item boundaries, and the accumulator is double-buffered
+// in TMEM so that the epilogue of item k overlaps the MMAs of item k+1.  The member plans (tensor
+// maps + parameters) sit in a device table, item ranges in the by-value header.
+constexpr int kMaxGroup = 16;
+constexpr int kMaxPStages = 12;
+struct alignas(64) GroupEntry {
+    CUtensorMap tmA, tmB;
+    ConvParams p;
+    int gx, gy;
+};
+struct GroupHeader {
+    int n;
+    int item_begin[kMaxGroup + 1];
+    int stages;
+    uint32_t slot_bytes;         // ring slot: max(a_stage + b_stage) over the members, multiple of 1024
+    uint32_t acc_cols;           // TMEM columns per accumulator buffer: max(m_tiles * n_tile)
+    uint32_t tmem_cols;          // allocation: power of two >= 2 * acc_cols
+};
+
+constexpr int kPGroupThreads = 320;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 / 6-9 two epilogue teams (alternate items)
+
+__global__ void __launch_bounds__(kPGroupThreads, 1)
+conv_umma_pgroup_kernel(const GroupEntry* __restrict__ table, const __grid_constant__ GroupHeader hdr) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ ConvParams s_p[kMaxGroup];
+    __shared__ int s_gx[kMaxGroup];
+    __shared__ __align__(16) float s_bias[kMaxGroup][256];        // all output channels of every member
+    __shared__ __align__(8) unsigned long long s_bar[2 * kMaxPStages + 4];
+    __shared__ uint32_t s_tmem;
+
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t full_bar = smem_u32(&s_bar[0]);
+    const uint32_t empty_bar = full_bar + 8u * kMaxPStages;
+    const uint32_t acc_full = empty_bar + 8u * kMaxPStages;       // 2 barriers
+    const uint32_t acc_empty = acc_full + 16u;                    // 2 barriers
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    const int n_members = hdr.n;
+    const int total = hdr.item_begin[n_members];
+    const int stages = hdr.stages;
+    const uint32_t slot = hdr.slot_bytes;
+
+    pdl_launch_dependents();             // the next launch of this stream may start its prologue
+    for (int e = 0; e < n_members; ++e) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&table[e].p);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_p[e]);
+        for (int i = threadIdx.x; i < (int)(sizeof(ConvParams) / 4); i += kPGroupThreads) dst[i] = src[i];
+        const int cout = table[e].p.Cout;
+        const float* bsrc = table[e].p.bias;
+        for (int i = threadIdx.x; i < cout; i += kPGroupThreads) s_bias[e][i] = bsrc[i];
+    }
+    if ((int)threadIdx.x < n_members) s_gx[threadIdx.x] = table[threadIdx.x].gx;
+    if (warp == 0) {
+        for (int s = lane; s < stages; s += 32) {
+            mbar_init(full_bar + 8u * s, 1);
+            mbar_init(empty_bar + 8u * s, 1);
+        }
+        if (lane < 2) {
+            mbar_init(acc_full + 8u * lane, 1);
+            mbar_init(acc_empty + 8u * lane, 4);                  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&s_tmem), hdr.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
+    pdl_wait();                          // activations / residuals / outputs below belong to earlier launches
+
+    // work item w -> (member e, tile, output-channel split)
+    auto member_of = [&](int w) {
+        int e = 0;
+        while (e + 1 < n_members && w >= hdr.item_begin[e + 1]) ++e;
+        return e;
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer (warp-wide control flow, one elected lane issues) =====
+        int s = 0;
+        uint32_t ph = 0;
+        for (int w = (int)blockIdx.x; w < total; w += (int)gridDim.x) {
+            const int e = member_of(w);
+            const ConvParams& p = s_p[e];
+            const CUtensorMap* tmA = &table[e].tmA;
+            const CUtensorMap* tmB = &table[e].tmB;
+            const int local = w - hdr.item_begin[e], gx = s_gx[e];
+            int t = local % gx;
+            const int by = local / gx;
+            const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+            const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+            const int n0 = t * p.tn, h0 = tile_h * p.th, w0 = tile_w * p.tw;
+            const int n_off = by * p.n_tile;
+            const int ksz = p.ksz, pad = ksz / 2, taps = ksz * ksz, n_chunks = p.n_chunks, chunk = p.chunk, stride = p.stride, Cout = p.Cout;
+            const uint32_t tx = p.tx_bytes, a_bytes = p.a_stage_bytes;
+            if (p.tl && lane == 0) atomicMin(p.tl, globaltimer_ns());
+            for (int tap = 0; tap < taps; ++tap) {
+                const int dy = tap / ksz - pad, dx = tap % ksz - pad;
+                for (int cc = 0; cc < n_chunks; ++cc) {
+                    mbar_wait(empty_bar + 8u * s, ph ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar + 8u * s, tx);
+                        tma_load_4d(ring + s * slot, tmA, full_bar + 8u * s, cc * chunk, w0 * stride + dx, h0 * stride + dy, n0);
+                        tma_load_2d(ring + s * slot + a_bytes, tmB, full_bar + 8u * s, cc * chunk, tap * Cout + n_off);
+                    }
+                    __syncwarp();
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (warp-wide control flow, one elected lane issues) =====
+        int s = 0, cnt = 0;
+        uint32_t ph = 0;
+        for (int w = (int)blockIdx.x; w < total; w += (int)gridDim.x, ++cnt) {
+            const int e = member_of(w);
+            const ConvParams& p = s_p[e];
+            const int ab = cnt & 1, use = cnt >> 1;
+            if (use > 0) {                                   // the epilogue of item cnt-2 has drained this buffer
+                mbar_wait(acc_empty + 8u * ab, (uint32_t)((use - 1) & 1));
+                tc_fence_after();
+            }
+            const uint32_t d_base = tmem_base + (uint32_t)ab * hdr.acc_cols;
+            const int ksteps = p.chunk / 16, m_tiles = p.m_tiles, n_tile = p.n_tile;
+            const int k_iters = p.ksz * p.ksz * p.n_chunks;
+            const uint32_t idesc = p.idesc, a_bytes = p.a_stage_bytes;
+            const uint64_t d0 = make_desc(0, p.row_bytes);
+            const uint32_t mt_step = (128u * p.row_bytes) >> 4;
+            for (int it = 0; it < k_iters; ++it) {
+                mbar_wait(full_bar + 8u * s, ph);
+                tc_fence_after();
+                const uint64_t ad0 = d0 + ((ring + s * slot) >> 4);
+                const uint64_t bd0 = d0 + ((ring + s * slot + a_bytes) >> 4);
+                if (elect_one()) {
+                    for (int mt = 0; mt < m_tiles; ++mt) {
+                        const uint64_t ad = ad0 + mt * mt_step;
+                        const uint32_t dt = d_base + mt * n_tile;
+                        umma_f16(dt, ad, bd0, idesc, it ? 1u : 0u);
+                        umma_f16(dt, ad + 2, bd0 + 2, idesc, 1u);
+                        if (ksteps == 4) {
+                            umma_f16(dt, ad + 4, bd0 + 4, idesc, 1u);
+                            umma_f16(dt, ad + 6, bd0 + 6, idesc, 1u);
+                        }
+                    }
+                    umma_commit(empty_bar + 8u * s);          // frees the stage when these MMAs retire
+                }
+                __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1u; }
+            }
+            if (elect_one()) umma_commit(acc_full + 8u * ab);
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> global =====
+        // team t drains items t, t+2, ... of this CTA from accumulator buffer t, so that the global-memory
+        // latency of one item's residual loads / stores overlaps the other team's item
+        const int grp = warp & 3;                          // TMEM lane group this warp may read
+        const int team = (warp - 2) >> 2;
+        const int et = ((int)threadIdx.x - 64) & 127;      // 0..127 inside the team
+        int cnt = team;
+        for (int w = (int)blockIdx.x + team * (int)gridDim.x; w < total; w += 2 * (int)gridDim.x, cnt += 2) {
+            const int e = member_of(w);
+            const ConvParams& p = s_p[e];
+            const int local = w - hdr.item_begin[e], gx = s_gx[e];
+            int t = local % gx;
+            const int by = local / gx;
+            const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+            const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+            const int n0 = t * p.tn, h0 = tile_h * p.th, w0 = tile_w * p.tw;
+            const int n_tile = p.n_tile, n_off = by * n_tile, m_tiles = p.m_tiles, up = p.up, Cout = p.Cout, relu = p.relu;
+            const __half* res = p.res;
+            __half* out = p.out;
+            const int ab = cnt & 1, use = cnt >> 1;
+            const float* bias_s = s_bias[e] + n_off;
+            const int Hout = p.Ho * up, Wout = p.Wo * up;
+            bool valid[2];
+            int pn[2], ph_[2], pw[2];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int R = mt * 128 + grp * 32 + lane;
+                pw[mt] = w0 + R % p.tw; ph_[mt] = h0 + (R / p.tw) % p.th; pn[mt] = n0 + R / (p.tw * p.th);
+                valid[mt] = mt < m_tiles && pn[mt] < p.P;
+            }
+            const bool direct = up == 1;
+            uint4 rq[8];
+            auto fetch_res = [&](int mt, int cg) {
+                const size_t o = ((((size_t)pn[mt] * Hout + ph_[mt]) * Wout) + pw[mt]) * Cout + n_off + cg;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (cg + q * 8 < n_tile) rq[q] = *reinterpret_cast<const uint4*>(res + o + q * 8);
+            };
+            if (direct && res && valid[0]) fetch_res(0, 0);
+            mbar_wait(acc_full + 8u * ab, (uint32_t)(use & 1));
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + ((uint32_t)(grp * 32) << 16) + (uint32_t)ab * hdr.acc_cols;
+            for (int mt = 0; mt < m_tiles; ++mt) {
+                for (int cg = 0; cg < n_tile; cg += 64) {
+                    if (direct && res && valid[mt] && (mt | cg)) fetch_res(mt, cg);
+#pragma unroll
+                    for (int cq = 0; cq < 4; ++cq) {
+                        const int c0 = cg + cq * 16;
+                        if (c0 >= n_tile) break;
+                        uint32_t r[16];
+                        tmem_ld16(t_base + (uint32_t)(mt * n_tile + c0), r);
+                        tmem_ld_wait();
+                        if (!valid[mt]) continue;
+                        float v[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]) + bias_s[c0 + q];
+                        for (int uy = 0; uy < up; ++uy)
+                            for (int ux = 0; ux < up; ++ux) {
+                                const size_t o = ((((size_t)pn[mt] * Hout + ph_[mt] * up + uy) * Wout) + pw[mt] * up + ux) * Cout + n_off + c0;
+                                float x[16];
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) x[q] = v[q];
+                                if (res) {
+                                    uint4 q0, q1;
+                                    if (direct) { q0 = rq[2 * cq]; q1 = rq[2 * cq + 1]; }
+                                    else {
+                                        q0 = *reinterpret_cast<const uint4*>(res + o);
+                                        q1 = *reinterpret_cast<const uint4*>(res + o + 8);
+                                    }
+                                    const __half2* h0p = reinterpret_cast<const __half2*>(&q0);
+                                    const __half2* h1p = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float2 f0 = __half22float2(h0p[q]), f1 = __half22float2(h1p[q]);
+                                        x[2 * q] += f0.x; x[2 * q + 1] += f0.y;
+                                        x[8 + 2 * q] += f1.x; x[8 + 2 * q + 1] += f1.y;
+                                    }
+                                }
+                                if (relu) {
+#pragma unroll
+                                    for (int q = 0; q < 16; ++q) x[q] = fmaxf(x[q], 0.f);
+                                }
+                                __align__(16) __half2 pk[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) pk[q] = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+                                *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(&pk[0]);
+                                *reinterpret_cast<uint4*>(out + o + 8) = *reinterpret_cast<const uint4*>(&pk[4]);
+                            }
+                    }
+                }
+            }
+            // accumulator buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty + 8u * ab) : "memory");
+            if (p.tl && et == 0) atomicMax(p.tl + 1, globaltimer_ns());
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, hdr.tmem_cols);
+    }
+}
 
 constexpr int kHaloW = 10;       // 8 output columns + 1 halo column each side
 constexpr int kMaxChunks = 8;
@@ -1097,7 +1367,7 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     return HBP_OK;
 }
 
-int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPlan** out) {
+int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPlan** out, bool for_group) {
     const HOp& op = m.ops[op_index];
     const HTensor& ti = m.tensors[op.in];
     const int Ho = ti.h / op.stride, Wo = ti.w / op.stride;
@@ -1108,6 +1378,7 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     if (!enc) { delete pl; hbp_set_error("cuTensorMapEncodeTiled unavailable"); return HBP_ERR_CUDA; }
     if (!(ctx->attr_flags & ATTR_UMMA)) {
         HBP_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_pgroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<2, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -1118,7 +1389,7 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
         HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         ctx->attr_flags |= ATTR_UMMA;
     }
-    if ((op.k == 3 || (op.k == 1 && env_int("HBP_HALO_1X1", 1))) && op.stride == 1 && op.up == 1 && halo_mode_enabled()) {
+    if (!for_group && (op.k == 3 || (op.k == 1 && env_int("HBP_HALO_1X1", 1))) && op.stride == 1 && op.up == 1 && halo_mode_enabled()) {
         bool ok = false;
         int st = plan_halo(ctx, m, op, capP, pl, &ok);
         if (st) { delete pl; return st; }
@@ -1132,12 +1403,20 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     if (!n_tile) { delete pl; hbp_set_error("no N tile for Cout=%d", op.cout); return HBP_ERR_INVALID; }
     // 1x1 convolutions are epilogue-bound (K is one or a few chunks): keep the accumulator at
     // <= 128 TMEM columns so that four CTAs share an SM and overlap each other's epilogues
-    if (op.k == 1) while (n_tile > 128 && n_tile % 32 == 0) n_tile /= 2;
+    if (op.k == 1 && !for_group) while (n_tile > 128 && n_tile % 32 == 0) n_tile /= 2;
+    // members of a persistent group share one ring of equal slots: every member's stage (A box + weight box)
+    // stays <= 24 KB so that eight of them are in flight (the loads are L2-latency bound)
+    if (for_group) {
+        const int cap_n = op.cin == 32 ? 128 : 64;
+        while (n_tile > cap_n && n_tile % 32 == 0) n_tile /= 2;
+    }
     // M tiles per CTA: 2 when that still leaves >= 2 CTAs per SM and TMEM stays <= 256 columns
     int m_tiles = 2, tn = 0, th = 0, tw = 0;
     {
-        bool ok2 = pick_tile(Ho, Wo, 2, &tn, &th, &tw) && 2 * n_tile <= (op.k == 1 ? 128 : 256);
-        if (ok2) {
+        bool ok2 = pick_tile(Ho, Wo, 2, &tn, &th, &tw) && 2 * n_tile <= ((op.k == 1 && !for_group) ? 128 : 256) &&
+                   !(for_group && op.cin != 32);
+        // (persistent walkers want few, large work items: no minimum CTA count, no extra N split)
+        if (ok2 && !for_group) {
             const long ctas = (long)((capP + tn - 1) / tn) * (Ho / th) * (Wo / tw) * (op.cout / n_tile);
             if (ctas < 2L * ctx->sm_count) ok2 = false;
         }
@@ -1146,7 +1425,7 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     // too few CTAs: split N further (down to 32)
     {
         long ctas = (long)((capP + tn - 1) / tn) * (Ho / th) * (Wo / tw) * (op.cout / n_tile);
-        while (ctas < ctx->sm_count && n_tile % 32 == 0 && n_tile > 32) { n_tile /= 2; ctas *= 2; }
+        while (!for_group && ctas < ctx->sm_count && n_tile % 32 == 0 && n_tile > 32) { n_tile /= 2; ctas *= 2; }
     }
     p.Ho = Ho; p.Wo = Wo; p.Cout = op.cout; p.up = op.up; p.relu = op.relu;
     p.tn = tn; p.th = th; p.tw = tw; p.m_tiles = m_tiles; p.n_tile = n_tile;
@@ -1202,6 +1481,101 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     }
     *out = pl;
     return HBP_OK;
+}
+
+struct UmmaGroup {
+    GroupEntry* d_table = nullptr;
+    std::vector<GroupEntry> h;
+    GroupHeader hdr;
+    size_t smem = 0;
+    int grid = 0;
+    int P = -1;
+    const void* tl = nullptr;
+};
+
+void umma_group_destroy(UmmaGroup* g) {
+    if (!g) return;
+    if (g->d_table) cudaFree(g->d_table);
+    delete g;
+}
+
+// one persistent launch over the work items of `members` (mode-0 plans in m.umma); `slot_index` keys the table
+static int group_launch(hbp_ctx* ctx, HrnetModel& m, int slot_index, const int* members, int n, int P, cudaStream_t st) {
+    if (n < 1 || n > kMaxGroup) { hbp_set_error("group of %d convolutions (max %d)", n, kMaxGroup); return HBP_ERR_INVALID; }
+    if ((int)m.groups.size() < (int)m.ops.size()) m.groups.resize(m.ops.size(), nullptr);
+    UmmaGroup*& g = m.groups[slot_index];
+    if (!g) {
+        g = new UmmaGroup();
+        g->h.resize(n);
+        HBP_CUDA(cudaMalloc(&g->d_table, sizeof(GroupEntry) * n));
+    }
+    if (g->P != P || g->tl != (const void*)m.d_timeline) {
+        // (re)build the table for this batch size.  Never inside a graph capture: the first forward of a
+        // (batch, buffers) key runs eagerly, the capture of the second one finds the table in place.
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        if (cs != cudaStreamCaptureStatusNone) { hbp_set_error("group table rebuilt inside a capture"); return HBP_ERR_STATE; }
+        int items = 0;
+        uint32_t slot = 0, acc = 0;
+        g->hdr.n = n;
+        for (int i = 0; i < n; ++i) {
+            const int oi = members[i];
+            const UmmaPlan* pl = m.umma[oi];
+            if (!pl || pl->prm.mode != 0) { hbp_set_error("group member %s has no mode-0 plan", m.ops[oi].name.c_str()); return HBP_ERR_STATE; }
+            GroupEntry& e = g->h[i];
+            e.tmA = pl->tmA; e.tmB = pl->tmB; e.p = pl->prm;
+            e.p.P = P;
+            e.p.tl = m.d_timeline ? m.d_timeline + 2 * oi : nullptr;
+            const int tiles_n = (P + e.p.tn - 1) / e.p.tn;
+            e.gx = tiles_n * e.p.tiles_h * e.p.tiles_w;
+            e.gy = pl->n_splits;
+            g->hdr.item_begin[i] = items;
+            items += e.gx * e.gy;
+            slot = std::max(slot, e.p.a_stage_bytes + e.p.b_stage_bytes);
+            acc = std::max(acc, (uint32_t)(e.p.m_tiles * e.p.n_tile));
+        }
+        for (int i = n; i <= kMaxGroup; ++i) g->hdr.item_begin[i] = items;
+        slot = (slot + 1023u) & ~1023u;
+        int stages = (int)((uint32_t)env_int("HBP_PGROUP_SMEM_KB", 192) * 1024u / slot);
+        if (stages > kMaxPStages) stages = kMaxPStages;
+        if (stages < 2 || acc > 256) { hbp_set_error("group does not fit: slot %u B, %u accumulator columns", slot, acc); return HBP_ERR_INVALID; }
+        uint32_t cols = 32;
+        while (cols < 2 * acc) cols *= 2;
+        g->hdr.stages = stages; g->hdr.slot_bytes = slot; g->hdr.acc_cols = acc; g->hdr.tmem_cols = cols;
+        g->smem = (size_t)stages * slot + 1024;
+        int sms = ctx->sm_count;
+        if (n == 1 && m.ops[members[0]].sm_share > 0.f) sms = std::max(1, (int)(m.ops[members[0]].sm_share * ctx->sm_count + 0.5f));
+        g->grid = std::min(items, sms);
+        HBP_CUDA(cudaMemcpyAsync(g->d_table, g->h.data(), sizeof(GroupEntry) * n, cudaMemcpyHostToDevice, st));
+        HBP_CUDA(cudaStreamSynchronize(st));
+        g->P = P;
+        g->tl = m.d_timeline;
+        if (getenv("HBP_CONV_TRACE"))
+            fprintf(stderr, "[pgroup] %s members=%d items=%d grid=%d stages=%d slot=%u acc_cols=%u tmem=%u smem=%zu\n",
+                    m.ops[slot_index].name.c_str(), n, items, g->grid, stages, slot, acc, cols, g->smem);
+    }
+    static const int pdl = env_int("HBP_PDL", 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)g->grid); cfg.blockDim = dim3(kPGroupThreads); cfg.dynamicSmemBytes = g->smem; cfg.stream = st;
+    // high scheduling priority: a group with few, large CTAs (the last links of the stride-2 chains) must not
+    // queue behind the thousands of small blocks of the upsample-add that runs beside it on another stream
+    static int prio = 1;
+    if (prio == 1) { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); prio = env_int("HBP_PGROUP_PRIO", 1) ? hi : 0; }
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributePriority;
+    at[0].val.priority = prio;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, conv_umma_pgroup_kernel, (const GroupEntry*)g->d_table, g->hdr);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return hbp_cuda_fail(e, "conv_umma_pgroup_kernel", __FILE__, __LINE__);
+    return HBP_OK;
+}
+
+int umma_group_launch(hbp_ctx* ctx, HrnetModel& m, int group_index, int P, cudaStream_t st) {
+    const HOp& gop = m.ops[group_index];
+    return group_launch(ctx, m, group_index, gop.members.data(), (int)gop.members.size(), P, st);
 }
 
 static void launch_halo(dim3 grid, size_t smem, cudaStream_t st, const UmmaPlan* pl, const ConvParams& p) {
@@ -1269,8 +1643,13 @@ int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, 
             return HBP_OK;
         }
     }
+    static const int persist0 = env_int("HBP_PERSIST0", 1);
     if (p.mode == 1) launch_halo(grid, pl->smem_bytes, st, pl, p);
-    else {
+    else if (persist0 && m.ops[op_index].persist && p.m_tiles * p.n_tile <= 256) {
+        // per-tap convolutions (stride 2, fused upsample) walk their tiles with persistent CTAs: a group of one
+        const int member = op_index;
+        return group_launch(ctx, m, op_index, &member, 1, P, st);
+    } else {
         static const int pdl = env_int("HBP_PDL", 1);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = pl->smem_bytes; cfg.stream = st;

@@ -169,78 +169,128 @@ void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const
         }
     }
     // fuse: y_i = relu( sum_j f_ij(x_j) ), f_ii = identity.  Terms from higher-resolution
-    // branches (j < i) are stride-2 conv chains whose last conv accumulates into y_i; terms
+    // branches (j < i) are chains of i-j stride-2 convs whose last link accumulates into y_i; terms
     // from lower-resolution branches (j > i) are 1x1 convs at LOW resolution followed by ONE
     // coalesced upsample-add over all of them (a scatter inside the conv epilogue serialises
     // up*up dependent load/store pairs per thread).
+    //
+    // The whole stage is scheduled by LEVEL: link k of every chain and all the 1x1 convs (level 1)
+    // are independent of each other, so each level is one grouped launch (OP_GROUP) and the
+    // upsample-adds of all outputs are one launch (OP_UPADD_GROUP).  A dependent kernel level of the
+    // captured graph costs ~10 us whatever its size, and the per-output chains used to put up to
+    // six of them (plus cross-stream edges) on the critical path of each of the eight fuse stages.
     B.join();
+    static const bool grouped = getenv("HBP_FUSE_GROUP") ? atoi(getenv("HBP_FUSE_GROUP")) != 0 : true;
     const int n_out = multi_scale_output ? nb : 1;
     std::vector<int> y(n_out);
-    // The terms of a fuse stage are independent strands (a stride-2 chain, a low-resolution 1x1 conv).
-    // HBP_FUSE_SPREAD=1 rotates them over the streams (they meet again through per-op events,
-    // HOp::wait_ops); measured slower than one stream per output -- the extra cross-stream edges cost
-    // more start latency than the shorter chains save (profiles/r01_fuse_spread.log) -- so it is off.
-    static const bool spread = getenv("HBP_FUSE_SPREAD") != nullptr;
-    int rr = 0;
-    auto next_stream = [&](int dflt) { return spread ? (rr++ % kStreams) : dflt; };
-    // outputs in descending order (the longest stride-2 chains are issued first, each on its own
-    // stream); the upsample-adds, which wait for everything, are issued last so that they do not sit
-    // in a stream ahead of an independent strand
-    std::vector<HOp> upadds;
-    for (int i = n_out - 1; i >= 0; --i) {
-        B.cur_stream = i;
+    for (int i = 0; i < n_out; ++i) {
         const HTensor ti = m.tensors[x[i]];
         y[i] = B.new_tensor(ti.c, ti.h, ti.w);
-        int res = x[i];                    // first term adds the identity branch
-        for (int j = 0; j < i; ++j) {
-            const int last = (i == nb - 1) && (j == i - 1);
-            int cur = x[j];
-            B.cur_stream = next_stream(i);
-            for (int k = 0; k < i - j; ++k) {
+    }
+    const int n_levels = std::max(1, n_out - 1);
+    std::vector<int> acc(n_out);                         // running sum of output i so far (starts at the identity term)
+    for (int i = 0; i < n_out; ++i) acc[i] = x[i];
+    std::vector<std::vector<int>> cur(n_out, std::vector<int>(nb, -1));   // chain (i, j): tensor its next link reads
+    for (int i = 0; i < n_out; ++i) for (int j = 0; j < i; ++j) cur[i][j] = x[j];
+    std::vector<std::vector<int>> lows(n_out);
+    std::vector<std::vector<int>> ups(n_out);
+    std::vector<int> temps;                              // intermediates, free after the closing join
+    std::vector<int> group_of_level(n_levels + 1, -1);
+    B.cur_stream = 0;
+    for (int L = 1; L <= n_levels; ++L) {
+        std::vector<int> members;
+        int join_flag = 0;
+        auto took = [&]() {
+            members.push_back((int)m.ops.size() - 1);
+            join_flag |= m.ops.back().join_before;
+            if (grouped) { m.ops.back().join_before = 0; m.ops.back().grouped = 1; }
+        };
+        for (int i = L; i < n_out; ++i) {
+            for (int j = 0; j + L <= i; ++j) {
+                const int k = L - 1;                     // link index inside chain (i, j) of length i - j
                 const std::string nm = pre + S(".fuse_layers.%d.%d.%d.0", i, j, k);
-                if (k == i - j - 1) {
-                    B.conv(nm, cur, ch[i], 3, 2, last, res, y[i]);
-                    if (cur != x[j]) B.release(cur, true);
+                if (L == i - j) {
+                    // last link: accumulate into y_i; the deepest chain (j = 0) of the lowest-resolution
+                    // output closes the sum (no upsample-add follows there) and applies the ReLU
+                    const int last = (i == nb - 1) && (j == 0);
+                    B.conv(nm, cur[i][j], ch[i], 3, 2, last, acc[i], y[i]);
+                    acc[i] = y[i];
                 } else {
-                    const int nxt = B.conv(nm, cur, ch[j], 3, 2, 1);
-                    if (cur != x[j]) B.release(cur, true);
-                    cur = nxt;
+                    const int nxt = B.conv(nm, cur[i][j], ch[j], 3, 2, 1);
+                    temps.push_back(nxt);
+                    cur[i][j] = nxt;
                 }
+                took();
             }
-            res = y[i];
         }
-        if (i < nb - 1) {
-            int lows[3] = {-1, -1, -1}, ups[3] = {1, 1, 1}, nl = 0;
-            for (int j = i + 1; j < nb; ++j) {
-                B.cur_stream = next_stream(i);
-                lows[nl] = B.conv(pre + S(".fuse_layers.%d.%d.0", i, j), x[j], ch[i], 1, 1, 0);
-                ups[nl++] = 1 << (j - i);
-            }
-            B.cur_stream = i;
+        if (L == 1) {
+            for (int i = 0; i < n_out && i < nb - 1; ++i)
+                for (int j = i + 1; j < nb; ++j) {
+                    const int t = B.conv(pre + S(".fuse_layers.%d.%d.0", i, j), x[j], ch[i], 1, 1, 0);
+                    temps.push_back(t);
+                    lows[i].push_back(t);
+                    ups[i].push_back(1 << (j - i));
+                    took();
+                }
+        }
+        if (grouped && !members.empty()) {
+            HOp g;
+            g.kind = OP_GROUP;
+            g.name = pre + S(".fuse_level%d", L);
+            g.members = members;
+            g.stream = 0;
+            g.join_before = join_flag;
+            m.ops.push_back(g);
+            group_of_level[L] = (int)m.ops.size() - 1;
+        }
+    }
+    // upsample-adds: output i (< nb-1) needs its 1x1 terms (level 1) and its chains (closed at level i)
+    {
+        const int n_up = std::min(n_out, nb - 1);
+        const int need_level = std::max(1, n_up - 1);
+        const bool side = grouped && need_level < n_levels;      // deeper chain levels still to run: beside them, on stream 1
+        std::vector<int> members;
+        int join_flag = 0;
+        for (int i = 0; i < n_up; ++i) {
             HOp op;
             op.kind = OP_UPADD;
             op.name = pre + S(".fuse_layers.%d.upadd", i);
-            op.in = lows[0]; op.in2 = lows[1]; op.in3 = lows[2];
-            op.up = ups[0]; op.up2 = ups[1]; op.up3 = ups[2];
-            op.res = res; op.out = y[i];
+            op.in = lows[i][0];
+            op.in2 = lows[i].size() > 1 ? lows[i][1] : -1;
+            op.in3 = lows[i].size() > 2 ? lows[i][2] : -1;
+            op.up = ups[i][0];
+            op.up2 = ups[i].size() > 1 ? ups[i][1] : 1;
+            op.up3 = ups[i].size() > 2 ? ups[i][2] : 1;
+            op.res = acc[i]; op.out = y[i];
             op.cin = op.cout = ch[i];
             op.relu = 1;
-            op.stream = B.cur_stream;
-            upadds.push_back(op);
+            op.stream = side ? 1 : 0;
+            op.join_before = B.pending_join ? 1 : 0;
+            if (B.pending_join) B.last_join_op = (int)m.ops.size();
+            B.pending_join = false;
+            join_flag |= op.join_before;
+            if (grouped) { op.join_before = 0; op.grouped = 1; }
+            m.ops.push_back(op);
+            B.wrote(op.out, (int)m.ops.size() - 1);
+            members.push_back((int)m.ops.size() - 1);
+        }
+        if (grouped && !members.empty()) {
+            HOp g;
+            g.kind = OP_UPADD_GROUP;
+            g.name = pre + ".fuse_upadd";
+            g.members = members;
+            g.stream = side ? 1 : 0;
+            g.join_before = join_flag;
+            if (side) {
+                g.wait_ops.push_back(group_of_level[need_level]);
+                m.ops[group_of_level[need_level]].signal = 1;
+            }
+            m.ops.push_back(g);
+            // program order = issue order: the side-stream launch is recorded after the deeper levels
+            // were pushed, but it only waits for `need_level` through its event
         }
     }
-    for (HOp& op : upadds) {
-        B.cur_stream = op.stream;
-        op.join_before = B.pending_join ? 1 : 0;
-        if (B.pending_join) B.last_join_op = (int)m.ops.size();
-        B.pending_join = false;
-        B.depend(op, op.in); B.depend(op, op.in2); B.depend(op, op.in3); B.depend(op, op.res);
-        m.ops.push_back(op);
-        B.wrote(op.out, (int)m.ops.size() - 1);
-        B.release(op.in, true);
-        if (op.in2 >= 0) B.release(op.in2, true);
-        if (op.in3 >= 0) B.release(op.in3, true);
-    }
+    for (int t : temps) B.release(t, false);
     for (int j = 0; j < nb; ++j) B.release(x[j], false);
     B.join();
     x = y;
@@ -265,6 +315,7 @@ void hrnet_build_program(HrnetModel& m) {
         m.ops.push_back(op);
     }
     int x = B.conv("conv2", m.ops[0].out, 64, 3, 2, 1);
+    m.ops.back().persist = 1;
     B.release(m.ops[0].out, true);
     // layer1: 4 Bottlenecks (64 -> 256)
     for (int b = 0; b < 4; ++b) {
@@ -291,6 +342,7 @@ void hrnet_build_program(HrnetModel& m) {
     xs[0] = B.conv("transition1.0.0", x, C, 3, 1, 1);
     B.cur_stream = 1;                  // independent of transition1.0: side by side, on the stream of the branch it feeds
     xs[1] = B.conv("transition1.1.0.0", x, 2 * C, 3, 2, 1);
+
     B.cur_stream = 0;
     B.release(x, false);
     B.join();
@@ -299,10 +351,12 @@ void hrnet_build_program(HrnetModel& m) {
     // transition2: new branch from the last branch
     B.cur_stream = 2;
     xs.push_back(B.conv("transition2.2.0.0", xs[1], 4 * C, 3, 2, 1));
+
     ch.push_back(4 * C);
     for (int mod = 0; mod < 4; ++mod) stage_module(B, S("stage3.%d", mod), xs, ch, true);
     B.cur_stream = 3;
     xs.push_back(B.conv("transition3.3.0.0", xs[2], 8 * C, 3, 2, 1));
+
     ch.push_back(8 * C);
     for (int mod = 0; mod < 3; ++mod) stage_module(B, S("stage4.%d", mod), xs, ch, mod < 2);
     // head
@@ -325,64 +379,95 @@ void hrnet_build_program(HrnetModel& m) {
 namespace {
 
 // conv1: NCHW fp16 (P,3,H,W) -> NHWC fp16 (P,H/2,W/2,64), 3x3 stride 2 pad 1, +bias, ReLU.
-// One thread per output pixel, all 64 output channels in registers; the 27 x 64 weights sit in
-// shared memory as [tap*3+ci][co] and are read as broadcast float4 (one LDS.128 per 4 FMAs: the
-// scalar-LDS version was shared-memory-issue bound).  100 MB written at batch 64: HBM-bound floor ~18 us.
+// K = 27 is far too thin for a TMA/tcgen05 pipeline and, as 1728 scalar FMAs per pixel, compute-bound on
+// the fp32 pipes (110 us at batch 64, against an HBM floor of ~18 us for the 100 MB written).  Each warp
+// therefore builds the im2col rows of its 32 pixels in shared memory (K padded to 32) and runs them
+// through warp-level mma.sync m16n8k16 (fp16 x fp16 -> fp32): 32 MMAs per warp.  The warp's 32 pixels
+// are 4 KB of contiguous output: staged in shared memory (XOR-swizzled 16-byte chunks) and written back
+// as fully coalesced 512-byte rows.
+constexpr int kStemLd = 40;      // halfs per im2col / weight row in shared memory (32 + 8: conflict-free fragment loads)
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 __global__ void __launch_bounds__(128)
 stem1_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const float* __restrict__ bias,
              __half* __restrict__ out, int P, int H, int W) {
-    __shared__ __align__(16) float s_w[27 * 64];      // [tap*3 + ci][co]
+    __shared__ __align__(16) __half s_w[64 * kStemLd];          // [co][k], k = tap*3 + ci, zero for k >= 27
     __shared__ __align__(16) float s_b[64];
-    for (int i = threadIdx.x; i < 64 * 27; i += blockDim.x) {
-        const int r = i / 64, co = i % 64, tap = r / 3, ci = r % 3;
-        s_w[i] = __half2float(w[((size_t)tap * 64 + co) * 3 + ci]);      // blob layout [tap][co][ci]
+    __shared__ __align__(16) __half s_a[4][32 * kStemLd];       // per warp: [pixel][k]
+    __shared__ __align__(16) uint4 s_out[4][32 * 8];
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+        const int co = i >> 5, k = i & 31;
+        s_w[co * kStemLd + k] = k < 27 ? w[((size_t)(k / 3) * 64 + co) * 3 + (k % 3)] : __float2half(0.f);   // blob layout [tap][co][ci]
     }
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_b[i] = bias[i];
-    __syncthreads();
-    // a warp's 32 pixels are 4 KB of contiguous output: staged in shared memory (XOR-swizzled 16-byte
-    // chunks) and written back as fully coalesced 512-byte rows instead of 32 scattered 16-byte pieces
-    __shared__ __align__(16) uint4 s_out[4][32 * 8];
     const int Ho = H / 2, Wo = W / 2;
     const size_t total = (size_t)P * Ho * Wo;
     const size_t pix_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = pix_raw < total;
-    const size_t pix = live ? pix_raw : total - 1;
+    const size_t pix = pix_raw < total ? pix_raw : total - 1;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((size_t)Wo * Ho));
-    float v[27];
+    // im2col row of this lane's pixel
+    {
+        __align__(16) __half v[32];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+        for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            const int hi = ho * 2 + dy - 1, wi = wo * 2 + dx - 1;
-            const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+            for (int dx = 0; dx < 3; ++dx) {
+                const int hi = ho * 2 + dy - 1, wi = wo * 2 + dx - 1;
+                const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
 #pragma unroll
-            for (int ci = 0; ci < 3; ++ci)
-                v[(dy * 3 + dx) * 3 + ci] = ok ? __half2float(__ldg(in + (((size_t)n * 3 + ci) * H + hi) * W + wi)) : 0.f;
-        }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {                      // 16 output channels at a time
-        float acc[16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_b + g * 16 + 4 * q);
-            acc[4 * q] = b4.x; acc[4 * q + 1] = b4.y; acc[4 * q + 2] = b4.z; acc[4 * q + 3] = b4.w;
-        }
-#pragma unroll
-        for (int t = 0; t < 27; ++t) {
-            const float4* ww = reinterpret_cast<const float4*>(s_w + t * 64 + g * 16);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 w4 = ww[q];
-                acc[4 * q] = fmaf(v[t], w4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v[t], w4.y, acc[4 * q + 1]);
-                acc[4 * q + 2] = fmaf(v[t], w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v[t], w4.w, acc[4 * q + 3]);
+                for (int ci = 0; ci < 3; ++ci)
+                    v[(dy * 3 + dx) * 3 + ci] = ok ? __ldg(in + (((size_t)n * 3 + ci) * H + hi) * W + wi) : __float2half(0.f);
             }
-        }
-        __align__(16) __half2 r[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) r[c] = __floats2half2_rn(fmaxf(acc[2 * c], 0.f), fmaxf(acc[2 * c + 1], 0.f));
-        s_out[wrp][lane * 8 + ((2 * g) ^ (lane & 7))] = *reinterpret_cast<const uint4*>(&r[0]);
-        s_out[wrp][lane * 8 + ((2 * g + 1) ^ (lane & 7))] = *reinterpret_cast<const uint4*>(&r[4]);
+        for (int k = 27; k < 32; ++k) v[k] = __float2half(0.f);
+        uint4* dst = reinterpret_cast<uint4*>(&s_a[wrp][lane * kStemLd]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4*>(v)[q];
+    }
+    __syncthreads();                                   // weights (block) + im2col rows (warp) visible
+    const int g = lane >> 2, tq = lane & 3;            // fragment row group / thread-in-quad
+    // A fragments: 2 M-tiles (16 pixels) x 2 K-steps
+    uint32_t a[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const __half* r0 = &s_a[wrp][(mt * 16 + g) * kStemLd + ks * 16 + tq * 2];
+            const __half* r1 = r0 + 8 * kStemLd;
+            a[mt][ks][0] = *reinterpret_cast<const uint32_t*>(r0);
+            a[mt][ks][1] = *reinterpret_cast<const uint32_t*>(r1);
+            a[mt][ks][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
+            a[mt][ks][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+        }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {                   // 8 output channels at a time
+        float acc[2][4];
+        const float2 bz = *reinterpret_cast<const float2*>(s_b + nt * 8 + tq * 2);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) { acc[mt][0] = bz.x; acc[mt][1] = bz.y; acc[mt][2] = bz.x; acc[mt][3] = bz.y; }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const __half* br = &s_w[(nt * 8 + g) * kStemLd + ks * 16 + tq * 2];
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(br), b1 = *reinterpret_cast<const uint32_t*>(br + 8);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_16816(acc[mt], a[mt][ks], b0, b1);
+        }
+        // C fragment: rows g / g+8 of the M-tile, channels nt*8 + tq*2 + {0,1} -> 16-byte chunk nt of the pixel, word tq
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int pl = mt * 16 + hf * 8 + g;
+                const __half2 r = __floats2half2_rn(fmaxf(acc[mt][2 * hf], 0.f), fmaxf(acc[mt][2 * hf + 1], 0.f));
+                reinterpret_cast<__half2*>(&s_out[wrp][pl * 8 + (nt ^ (pl & 7))])[tq] = r;
+            }
     }
     __syncwarp();
     const size_t warp_pix0 = (size_t)blockIdx.x * blockDim.x + wrp * 32;
@@ -480,6 +565,67 @@ upsample_add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, 
             pk[k] = __floats2half2_rn(x0, x1);
         }
         *reinterpret_cast<uint4*>(out + idx[u] * 8) = *reinterpret_cast<const uint4*>(pk);
+    }
+}
+
+// All upsample-adds of one fuse stage as one launch: blockIdx.y picks the output.
+struct UpaddProblem {
+    const __half *a, *b, *c, *res;
+    __half* out;
+    int H, W, C, fa, fb, fc, relu;
+    unsigned blocks;
+};
+struct UpaddGroup { UpaddProblem p[3]; };
+
+__global__ void __launch_bounds__(256)
+upsample_add_group_kernel(const __grid_constant__ UpaddGroup g, int P) {
+    const UpaddProblem& q = g.p[blockIdx.y];
+    if (blockIdx.x >= q.blocks) return;
+    const int H = q.H, W = q.W, C = q.C;
+    const int c8n = C >> 3;
+    const size_t total = (size_t)P * H * W * c8n;
+    const size_t half_n = (total + 1) >> 1;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= half_n) return;
+    const size_t idx[2] = {i0, i0 + half_n};
+    uint4 v[2][4];
+    bool on[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        on[u] = idx[u] < total;
+        if (!on[u]) continue;
+        const int c8 = (int)(idx[u] % c8n);
+        const size_t pix = idx[u] / c8n;
+        const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
+        auto src = [&](const __half* s, int f) {
+            const int hs = H / f, ws = W / f;
+            return __ldg(reinterpret_cast<const uint4*>(s + (((size_t)n * hs + h / f) * ws + w / f) * C + c8 * 8));
+        };
+        v[u][0] = *reinterpret_cast<const uint4*>(q.res + pix * C + c8 * 8);
+        v[u][1] = src(q.a, q.fa);
+        if (q.b) v[u][2] = src(q.b, q.fb);
+        if (q.c) v[u][3] = src(q.c, q.fc);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        if (!on[u]) continue;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        auto add = [&](const uint4& t4) {
+            const __half2* hq = reinterpret_cast<const __half2*>(&t4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float2 t = __half22float2(hq[k]); acc[2 * k] += t.x; acc[2 * k + 1] += t.y; }
+        };
+        add(v[u][0]); add(v[u][1]);
+        if (q.b) add(v[u][2]);
+        if (q.c) add(v[u][3]);
+        __align__(16) __half2 pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float x0 = acc[2 * k], x1 = acc[2 * k + 1];
+            if (q.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+            pk[k] = __floats2half2_rn(x0, x1);
+        }
+        *reinterpret_cast<uint4*>(q.out + idx[u] * 8) = *reinterpret_cast<const uint4*>(pk);
     }
 }
 
@@ -596,6 +742,8 @@ static void free_batch_state(hbp_ctx* ctx, HrnetModel* m) {
     if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
     for (UmmaPlan* p : m->umma) if (p) umma_plan_destroy(p);
     m->umma.clear();
+    for (UmmaGroup* g : m->groups) if (g) umma_group_destroy(g);
+    m->groups.clear();
     for (__half* b : m->bufs) if (b) cudaFree(b);
     m->bufs.clear();
     m->cap_P = 0;
@@ -663,6 +811,7 @@ static int ensure_batch(hbp_ctx* ctx, HrnetModel* m, int P) {
         HBP_CUDA(cudaMalloc(&m->bufs[b], m->buf_elems_per_image[b] * (size_t)cap * sizeof(__half)));
     m->cap_P = cap;
     m->umma.assign(m->ops.size(), nullptr);
+    m->groups.assign(m->ops.size(), nullptr);
     return HBP_OK;
 }
 
@@ -705,8 +854,37 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
         tev.resize(2 * m->ops.size());
         for (auto& e : tev) cudaEventCreate(&e);
     }
+    // one op (conv / upsample-add) on stream `st`; the groups below fall back to this per member
+    auto issue_upadd = [&](const HOp& op, cudaStream_t st) {
+        const HTensor& to = m->tensors[op.out];
+        const size_t total = ((size_t)P * to.h * to.w * (to.c / 8) + 1) / 2;      // two items per thread
+        upsample_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            m->bufs[m->tensors[op.in].buf], op.in2 >= 0 ? m->bufs[m->tensors[op.in2].buf] : nullptr,
+            op.in3 >= 0 ? m->bufs[m->tensors[op.in3].buf] : nullptr, m->bufs[m->tensors[op.res].buf],
+            m->bufs[to.buf], P, to.h, to.w, to.c, op.up, op.up2, op.up3, op.relu);
+    };
+    auto issue_conv = [&](size_t i, cudaStream_t st) -> int {
+        const HOp& op = m->ops[i];
+        if (m->engine == 1 && umma_supported(*m, op)) {
+            if (!m->umma[i]) {
+                int s = umma_plan_create(ctx, *m, (int)i, m->cap_P, &m->umma[i]);
+                if (s) return s;
+            }
+            return umma_launch(ctx, *m, (int)i, m->umma[i], P, st);
+        }
+        const HTensor& ti = m->tensors[op.in];
+        const int Ho = ti.h / op.stride, Wo = ti.w / op.stride;
+        const size_t total = (size_t)P * Ho * Wo;
+        dim3 grid((unsigned)((total + kTP - 1) / kTP), (op.cout + kTC - 1) / kTC);
+        conv_simt_kernel<<<grid, 256, 0, st>>>(
+            m->bufs[ti.buf], m->d_weights + op.w_off, m->d_bias + op.b_off,
+            op.res >= 0 ? m->bufs[m->tensors[op.res].buf] : nullptr, m->bufs[m->tensors[op.out].buf],
+            P, ti.h, ti.w, op.cin, Ho, Wo, op.cout, op.k, op.stride, op.up, op.relu);
+        return HBP_OK;
+    };
     for (size_t i = 0; i < m->ops.size(); ++i) {
         const HOp& op = m->ops[i];
+        if (op.grouped) continue;            // issued by the group op that lists it
         if (op.join_before) { int s = join_all(ctx, m); if (s) return s; }
         cudaStream_t st = stream_of(ctx, m, op.stream);
         for (int w : op.wait_ops) HBP_CUDA(cudaStreamWaitEvent(st, m->ev_pool[w], 0));
@@ -729,33 +907,45 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
                 head_kernel<float><<<(unsigned)((total + 127) / 128), 128, sm, st>>>(
                     m->bufs[ti.buf], m->d_weights + op.w_off, m->d_bias + op.b_off, (float*)heatmaps, P, ti.h * ti.w, ti.c);
         } else if (op.kind == OP_UPADD) {
-            const HTensor& to = m->tensors[op.out];
-            const size_t total = ((size_t)P * to.h * to.w * (to.c / 8) + 1) / 2;      // two items per thread
-            upsample_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-                m->bufs[m->tensors[op.in].buf], op.in2 >= 0 ? m->bufs[m->tensors[op.in2].buf] : nullptr,
-                op.in3 >= 0 ? m->bufs[m->tensors[op.in3].buf] : nullptr, m->bufs[m->tensors[op.res].buf],
-                m->bufs[to.buf], P, to.h, to.w, to.c, op.up, op.up2, op.up3, op.relu);
-        } else {
-            bool done = false;
-            if (m->engine == 1 && umma_supported(*m, op)) {
-                if (!m->umma[i]) {
-                    int s = umma_plan_create(ctx, *m, (int)i, m->cap_P, &m->umma[i]);
-                    if (s) return s;
-                }
-                int s = umma_launch(ctx, *m, (int)i, m->umma[i], P, st);
+            issue_upadd(op, st);
+        } else if (op.kind == OP_UPADD_GROUP) {
+            if (op.members.size() > 3) { hbp_set_error("upsample-add group of %zu", op.members.size()); return HBP_ERR_INVALID; }
+            UpaddGroup g = {};
+            unsigned max_blocks = 0;
+            for (size_t k = 0; k < op.members.size(); ++k) {
+                const HOp& u = m->ops[op.members[k]];
+                const HTensor& to = m->tensors[u.out];
+                UpaddProblem& q = g.p[k];
+                q.a = m->bufs[m->tensors[u.in].buf];
+                q.b = u.in2 >= 0 ? m->bufs[m->tensors[u.in2].buf] : nullptr;
+                q.c = u.in3 >= 0 ? m->bufs[m->tensors[u.in3].buf] : nullptr;
+                q.res = m->bufs[m->tensors[u.res].buf];
+                q.out = m->bufs[to.buf];
+                q.H = to.h; q.W = to.w; q.C = to.c; q.fa = u.up; q.fb = u.up2; q.fc = u.up3; q.relu = u.relu;
+                const size_t total = ((size_t)P * to.h * to.w * (to.c / 8) + 1) / 2;
+                q.blocks = (unsigned)((total + 255) / 256);
+                max_blocks = std::max(max_blocks, q.blocks);
+            }
+            upsample_add_group_kernel<<<dim3(max_blocks, (unsigned)op.members.size()), 256, 0, st>>>(g, P);
+        } else if (op.kind == OP_GROUP) {
+            // grouped launch when every member runs on the tensor engine; member by member otherwise
+            bool all = m->engine == 1;
+            for (int k : op.members) all = all && umma_supported(*m, m->ops[k]);
+            if (all) {
+                for (int k : op.members)
+                    if (!m->umma[k]) {
+                        int s = umma_plan_create(ctx, *m, k, m->cap_P, &m->umma[k], /*for_group=*/true);
+                        if (s) return s;
+                    }
+                int s = umma_group_launch(ctx, *m, (int)i, P, st);
                 if (s) return s;
-                done = true;
+            } else {
+                for (int k : op.members) { int s = issue_conv((size_t)k, st); if (s) return s; launches++; }
+                --launches;
             }
-            if (!done) {
-                const HTensor& ti = m->tensors[op.in];
-                const int Ho = ti.h / op.stride, Wo = ti.w / op.stride;
-                const size_t total = (size_t)P * Ho * Wo;
-                dim3 grid((unsigned)((total + kTP - 1) / kTP), (op.cout + kTC - 1) / kTC);
-                conv_simt_kernel<<<grid, 256, 0, st>>>(
-                    m->bufs[ti.buf], m->d_weights + op.w_off, m->d_bias + op.b_off,
-                    op.res >= 0 ? m->bufs[m->tensors[op.res].buf] : nullptr, m->bufs[m->tensors[op.out].buf],
-                    P, ti.h, ti.w, op.cin, Ho, Wo, op.cout, op.k, op.stride, op.up, op.relu);
-            }
+        } else {
+            int s = issue_conv(i, st);
+            if (s) return s;
         }
         ++launches;
         if (op.signal) {
@@ -893,6 +1083,8 @@ int hrnet_single_conv(hbp_ctx* ctx, int engine, const __half* in, int P, int H, 
         UmmaPlan* plan = nullptr;
         status = umma_plan_create(ctx, m, 0, P, &plan);
         if (status == HBP_OK) {
+            m.umma = {plan};
+            m.ops[0].persist = 1;
             status = umma_launch(ctx, m, 0, plan, P, ctx->stream);
             if (iters > 0 && avg_ms && status == HBP_OK) {
                 // timing (bring-up / microbenchmark): the launches are captured into one CUDA graph so
@@ -944,6 +1136,11 @@ int hrnet_single_conv(hbp_ctx* ctx, int engine, const __half* in, int P, int H, 
         if (used_engine) *used_engine = 0;
     }
     m.d_weights = nullptr; m.d_bias = nullptr; m.bufs.clear();
+    if (!m.groups.empty()) {
+        cudaStreamSynchronize(ctx->stream);
+        for (UmmaGroup* g : m.groups) if (g) umma_group_destroy(g);
+        m.groups.clear();
+    }
     ctx->launches++;
     return status;
 }
@@ -962,7 +1159,7 @@ extern "C" int hbp_hrnet_describe(int width, int in_h, int in_w, char* buf, size
     std::string s;
     char line[256];
     for (const HOp& op : m.ops) {
-        if (op.kind == OP_UPADD) continue;            // no parameters
+        if (op.kind == OP_UPADD || op.kind == OP_GROUP || op.kind == OP_UPADD_GROUP) continue;            // no parameters
         int ho = 0, wo = 0;
         if (op.kind == OP_STEM1) { ho = m.in_h / 2; wo = m.in_w / 2; }
         else { ho = m.tensors[op.in].h / op.stride; wo = m.tensors[op.in].w / op.stride; }

@@ -12,7 +12,10 @@ struct HTensor {
     int buf = -1;               // index into the per-batch buffer table
 };
 
-enum HOpKind { OP_STEM1 = 0, OP_CONV = 1, OP_HEAD = 2, OP_UPADD = 3 };
+enum HOpKind { OP_STEM1 = 0, OP_CONV = 1, OP_HEAD = 2, OP_UPADD = 3,
+               OP_GROUP = 4,        // one launch that runs `members` (independent OP_CONV ops of one fuse level)
+               OP_UPADD_GROUP = 5   // one launch that runs `members` (the OP_UPADD ops of one fuse stage)
+};
 
 // out = act( conv_k,s(in) + bias [+ residual] ), optionally replicated `up` x `up`
 // (nearest upsample fused into the store; residual is read at the upsampled position)
@@ -30,9 +33,13 @@ struct HOp {
     float sm_share = 0.f;       // > 0: fraction of the SMs this op's persistent launch may occupy (branches run side by side)
     std::vector<int> wait_ops;  // ops on OTHER streams that must have finished first (producers of this op's inputs since the last join)
     int signal = 0;             // some later op waits for this one: record an event after it
+    int persist = 0;            // per-tap conv that owns the GPU while it runs: persistent tile walkers (conv_umma_pgroup_kernel)
+    int grouped = 0;            // issued by the OP_GROUP / OP_UPADD_GROUP op that lists it in `members`
+    std::vector<int> members;   // OP_GROUP / OP_UPADD_GROUP: indices of the member ops
 };
 
 struct UmmaPlan;                // conv_umma.cu: per-op tensor maps + tile shape (per batch size)
+struct UmmaGroup;               // conv_umma.cu: device table of the member plans of one OP_GROUP launch
 
 struct HrnetModel {
     int width = 32, in_h = 256, in_w = 192;
@@ -48,6 +55,7 @@ struct HrnetModel {
     int cap_P = 0;
     std::vector<__half*> bufs;
     std::vector<UmmaPlan*> umma;                // one per op (nullptr = SIMT)
+    std::vector<UmmaGroup*> groups;             // one per op (OP_GROUP ops only)
     cudaGraphExec_t graph_exec = nullptr;
     int graph_P = 0, graph_dtype = -1, graph_engine = -1;
     const void* graph_in = nullptr;
@@ -65,6 +73,9 @@ void hrnet_build_program(HrnetModel& m);
 
 // conv_umma.cu
 bool umma_supported(const HrnetModel& m, const HOp& op);
-int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int P, UmmaPlan** out);
+int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int P, UmmaPlan** out, bool for_group = false);
 void umma_plan_destroy(UmmaPlan* p);
 int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* plan, int P, cudaStream_t st);
+// one launch for all member convs of the OP_GROUP op `group_index` (plans in m.umma, created with for_group)
+int umma_group_launch(hbp_ctx* ctx, HrnetModel& m, int group_index, int P, cudaStream_t st);
+void umma_group_destroy(UmmaGroup* g);
