@@ -30,6 +30,8 @@ namespace {
 constexpr int kBandRows = 8;
 constexpr int kThreads = 256;
 constexpr int kSmemBudget = 28 * 1024;    // per CTA: 7 CTAs of 256 threads per SM
+constexpr int kSmemPad = 16;              // bytes in front of / behind the staged box: a zero-weight tap may read up to 3 bytes outside it
+constexpr int kMaxTabW = 512;             // output widths up to this use the per-CTA column tables
 
 struct Affine {
     double m00, m01, m02, m10, m11, m12;
@@ -63,12 +65,33 @@ __device__ __forceinline__ OutT to_out(float v);
 template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
 
+// Integer accumulator (sum of byte x weight in 1/1024 units, carried in the mantissa of 2^23: bits 0x4B000000 | acc)
+// -> acc / 1024 / 255 in the output type.  fp32: exact int -> float, correctly rounded /255, exact 2^-10.
+// fp16: ONE fused multiply-add, RN(acc * RN(1/261120)), gives the same fp16 value as rounding the correctly
+// rounded fp32 quotient for every possible accumulator 0..261120 (exhaustive check: tests/test_host_cpu.py).
+template <typename OutT>
+__device__ __forceinline__ OutT finish_acc(unsigned bits);
+template <> __device__ __forceinline__ float finish_acc<float>(unsigned bits) {
+    return div255(__uint_as_float(bits) - 8388608.0f) * 0.0009765625f;
+}
+template <> __device__ __forceinline__ __half finish_acc<__half>(unsigned bits) {
+    const float y = 1.0f / 261120.0f;
+    return __float2half_rn(__fmaf_rn(__uint_as_float(bits), y, -8388608.0f * y));
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads)
 crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
                  const double* __restrict__ Ms, const int* __restrict__ frame_idx, int P,
                  int out_h, int out_w, int swap_rb, OutT* __restrict__ out) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem_all[];
+    uint8_t* const smem = smem_all + kSmemPad;
+    __shared__ int s_ad[kMaxTabW], s_bd[kMaxTabW];      // OpenCV's adelta / bdelta tables (per output column)
+    // axis-aligned maps (every crop_and_resize box): per column the staged byte offset of the left tap and the
+    // packed x-weights, rebuilt per pass (they depend on the pass's box)
+    __shared__ __align__(16) int s_cx3[kMaxTabW];
+    __shared__ __align__(16) unsigned s_wx[kMaxTabW];
+    __shared__ int s_srow[2 * kBandRows];
     __shared__ int s_box[4];        // sx_min, sy_min, cols, rows (clamped to the frame)
     __shared__ int s_use_smem;
 
@@ -80,6 +103,13 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
         const double* m = Ms + (size_t)p * 6;
         A.m00 = m[0]; A.m01 = m[1]; A.m02 = m[2]; A.m10 = m[3]; A.m11 = m[4]; A.m12 = m[5];
     }
+    const bool tab = out_w <= kMaxTabW;
+    const bool axis = tab && A.m01 == 0.0 && A.m10 == 0.0;
+    if (tab)
+        for (int x = threadIdx.x; x < out_w; x += kThreads) {
+            s_ad[x] = __double2int_rn(__dmul_rn(__dmul_rn(A.m00, (double)x), 1024.0));
+            s_bd[x] = __double2int_rn(__dmul_rn(__dmul_rn(A.m10, (double)x), 1024.0));
+        }
     int f = frame_idx[p];
     f = f < 0 ? 0 : (f >= n_frames ? n_frames - 1 : f);
     const uint8_t* __restrict__ src = frames + (size_t)f * H * W * 3;
@@ -106,7 +136,10 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
         xmax = min(xmax, W - 1); ymax = min(ymax, H - 1);
         const int cols = xmax - xmin + 1, nrows = ymax - ymin + 1;
         box[0] = xmin; box[1] = ymin; box[2] = cols; box[3] = nrows;
-        *need = (cols > 0 && nrows > 0) ? (long long)nrows * (((long long)cols * 3 + 15 + 15) / 16 * 16) : 0;
+        // axis-aligned maps stage only the two source rows every output row taps when that is fewer rows
+        // than the whole span (down-scaling by more than 2 vertically)
+        const int srows = axis ? min(nrows, 2 * nr) : nrows;
+        *need = (cols > 0 && nrows > 0) ? (long long)srows * (((long long)cols * 3 + 15 + 15) / 16 * 16) : 0;
     };
     if (threadIdx.x == 0) {
         int rp = kBandRows;
@@ -137,6 +170,27 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
     const bool staged = s_use_smem != 0;
     const int pitch = ((bcols * 3 + 15 + 15) / 16) * 16;   // bytes per staged row
 
+    const bool slots = staged && axis && brows > 2 * prow;      // staged row 2*ry + t = source row of tap t of output row pr0 + ry
+    const int srows = slots ? 2 * prow : brows;
+    if (slots) {
+        if (threadIdx.x < 2 * prow) {
+            const int y = pr0 + ((int)threadIdx.x >> 1);
+            const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(A.m11, (double)y), A.m12), 1024.0)) + 16;
+            const int sy = (Y0 >> 5) >> 5;
+            s_srow[threadIdx.x] = min(max(sy + ((int)threadIdx.x & 1), by0), by0 + brows - 1);
+        }
+        __syncthreads();
+    }
+    if (staged && axis) {
+        const int X0c = __double2int_rn(__dmul_rn(A.m02, 1024.0)) + 16;
+        for (int x = threadIdx.x; x < ((out_w + 7) & ~7); x += kThreads) {
+            const int X = (X0c + s_ad[min(x, out_w - 1)]) >> 5;
+            const int sx = X >> 5, fx = X & 31;
+            const unsigned wx0 = (unsigned)sx < (unsigned)W ? 32u - fx : 0u, wx1 = (unsigned)(sx + 1) < (unsigned)W ? (unsigned)fx : 0u;
+            s_cx3[x] = (min(max(sx, bx0 - 1), bx0 + bcols - 1) - bx0) * 3;
+            s_wx[x] = wx0 | (wx1 << 16);
+        }
+    }
     if (staged) {
         // Stage rows [by0, by0+brows) x byte range of columns [bx0, bx0+bcols).
         // Row r lives at smem[r*pitch + (addr & 15) ...]: the copy is done in
@@ -144,7 +198,7 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
         // sub-16 phase `ph`; taps index with that phase.
         const int chunks_per_row = pitch / 16;
         const uint8_t* frame_end = frames + (size_t)n_frames * H * W * 3;
-        const int n_chunks = brows * chunks_per_row;
+        const int n_chunks = srows * chunks_per_row;
         // four 16-byte loads in flight per thread before the first shared-memory store: the copy
         // is latency-bound otherwise (one DRAM round trip per loop iteration)
         for (int t0 = threadIdx.x; t0 < n_chunks; t0 += 4 * kThreads) {
@@ -157,7 +211,7 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
                 off[u] = -1;
                 if (t >= n_chunks) continue;
                 const int r = t / chunks_per_row, c = t - r * chunks_per_row;
-                const uint8_t* g0 = src + ((size_t)(by0 + r) * W + bx0) * 3;
+                const uint8_t* g0 = src + ((size_t)(slots ? s_srow[r] : by0 + r) * W + bx0) * 3;
                 const uint8_t* ga = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(g0) & ~uintptr_t(15)) + 16 * c;
                 off[u] = r * pitch + 16 * c;
                 if (ga >= frames && ga + 16 <= frame_end) {
@@ -175,6 +229,61 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
         __syncthreads();
     }
 
+    if (staged && axis) {
+        // axis-aligned: one warp per output row, a lane takes pixel pairs x = 2*lane + 64*j.  The row terms
+        // (sy, fy, staged row bases) are per warp-row, the column terms come from the per-pass tables, and
+        // neighbouring lanes read neighbouring staged bytes (the 8-pixels-per-thread layout of the general
+        // path puts lanes 8 pixels apart: 4-way shared-memory bank conflicts).  ~35 instructions per pixel.
+        const int src_lo = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+        const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+        for (int ry = wrp; ry < prow; ry += kThreads / 32) {
+            const int y = pr0 + ry;
+            const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(A.m11, (double)y), A.m12), 1024.0)) + 16;
+            const int Y = Y0 >> 5, sy = Y >> 5, fy = Y & 31;
+            const unsigned wy0 = (unsigned)sy < (unsigned)H ? 32u - fy : 0u, wy1 = (unsigned)(sy + 1) < (unsigned)H ? (unsigned)fy : 0u;
+            const int r0 = min(max(sy, by0), by0 + brows - 1), r1 = min(max(sy + 1, by0), by0 + brows - 1);
+            const int base0 = (slots ? 2 * ry : r0 - by0) * pitch + ((src_lo + (r0 * W + bx0) * 3) & 15);
+            const int base1 = (slots ? 2 * ry + 1 : r1 - by0) * pitch + ((src_lo + (r1 * W + bx0) * 3) & 15);
+            OutT* orow = obase + (size_t)y * out_w;
+            for (int x0 = 2 * lane; x0 < out_w; x0 += 64) {
+                const int2 c3 = *reinterpret_cast<const int2*>(&s_cx3[x0]);
+                const uint2 wx = *reinterpret_cast<const uint2*>(&s_wx[x0]);
+                OutT r[3][2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int cc = k ? c3.y : c3.x;
+                    const unsigned wxx = k ? wx.y : wx.x;
+                    const unsigned wr0 = wxx * wy0, wr1 = wxx * wy1;
+                    unsigned acc0 = 0x4B000000u, acc1 = 0x4B000000u, acc2 = 0x4B000000u;
+                    auto row = [&](int b, unsigned wr) {
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(smem + (b & ~3));
+                        const uint32_t lo = wp[0], mid = wp[1], hi = wp[2];
+                        const unsigned sh = (unsigned)b << 3;                  // funnel shift takes the amount mod 32
+                        const uint32_t v0 = __funnelshift_r(lo, mid, sh), v1 = __funnelshift_r(mid, hi, sh);
+                        acc0 = __dp2a_lo(wr, __byte_perm(v0, v1, 0x4430), acc0);
+                        acc1 = __dp2a_lo(wr, __byte_perm(v0, v1, 0x4441), acc1);
+                        acc2 = __dp2a_lo(wr, __byte_perm(v0, v1, 0x4452), acc2);
+                    };
+                    row(base0 + cc, wr0);
+                    row(base1 + cc, wr1);
+                    r[0][k] = finish_acc<OutT>(swap_rb ? acc2 : acc0);
+                    r[1][k] = finish_acc<OutT>(acc1);
+                    r[2][k] = finish_acc<OutT>(swap_rb ? acc0 : acc2);
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    OutT* o = orow + c * plane + x0;
+                    if (x0 + 1 < out_w && (reinterpret_cast<uintptr_t>(o) & (2 * sizeof(OutT) - 1)) == 0) {
+                        if (sizeof(OutT) == 2) *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(r[c]);
+                        else *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(r[c]);
+                    } else {
+                        o[0] = r[c][0];
+                        if (x0 + 1 < out_w) o[1] = r[c][1];
+                    }
+                }
+            }
+        }
+    } else
     for (int t = threadIdx.x; t < prow * groups; t += kThreads) {
         const int ry = t / groups, gx = t - ry * groups;
         const int y = pr0 + ry, xbeg = gx * 8;
@@ -182,6 +291,44 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
         // per-row constants
         const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(A.m01, (double)y), A.m02), 1024.0)) + 16;
         const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(A.m11, (double)y), A.m12), 1024.0)) + 16;
+        if (staged && tab) {
+            // Integer blend: the bilinear weights are (32-fy|fy) x (32-fx|fx) in 1/1024 units and the taps are
+            // bytes, so sum(b*w) <= 255*1024 is exact in int32 and equals 1024 x the float32 sum of the
+            // reference arithmetic (which is exact as well).  Out-of-frame taps get weight 0 and a clamped
+            // address.  The two x-taps of a row are 6 consecutive bytes: three aligned 32-bit loads, two
+            // funnel shifts, one PRMT + one DP2A per channel and row.
+            const int src_lo = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int x = min(xbeg + k, out_w - 1);
+                const int X = (X0 + s_ad[x]) >> 5, Y = (Y0 + s_bd[x]) >> 5;
+                const int sx = X >> 5, sy = Y >> 5;
+                const int fx = X & 31, fy = Y & 31;
+                const unsigned wx0 = (unsigned)sx < (unsigned)W ? 32u - fx : 0u, wx1 = (unsigned)(sx + 1) < (unsigned)W ? (unsigned)fx : 0u;
+                const unsigned wy0 = (unsigned)sy < (unsigned)H ? 32u - fy : 0u, wy1 = (unsigned)(sy + 1) < (unsigned)H ? (unsigned)fy : 0u;
+                const unsigned wx = wx0 | (wx1 << 16);                   // packed pair; products below stay < 2^16 per half
+                const unsigned wr0 = wx * wy0, wr1 = wx * wy1;
+                const int cx = min(max(sx, bx0 - 1), bx0 + bcols - 1) - bx0;          // -1 .. bcols-1 (the pad covers -1 and the right overhang)
+                const int r0 = min(max(sy, by0), by0 + brows - 1), r1 = min(max(sy + 1, by0), by0 + brows - 1);
+                unsigned acc[3] = {0x4B000000u, 0x4B000000u, 0x4B000000u};
+                auto row = [&](int yy, unsigned wr) {
+                    const int ph = (src_lo + (yy * W + bx0) * 3) & 15;
+                    const int b = (yy - by0) * pitch + ph + cx * 3;
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(smem + (b & ~3));
+                    const uint32_t lo = wp[0], mid = wp[1], hi = wp[2];
+                    const unsigned sh = (unsigned)(b & 3) * 8u;
+                    const uint32_t v0 = __funnelshift_r(lo, mid, sh), v1 = __funnelshift_r(mid, hi, sh);
+                    acc[0] = __dp2a_lo(wr, __byte_perm(v0, v1, 0x4430), acc[0]);
+                    acc[1] = __dp2a_lo(wr, __byte_perm(v0, v1, 0x4441), acc[1]);
+                    acc[2] = __dp2a_lo(wr, __byte_perm(v0, v1, 0x4452), acc[2]);
+                };
+                row(r0, wr0);
+                row(r1, wr1);
+                res[0][k] = finish_acc<OutT>(swap_rb ? acc[2] : acc[0]);
+                res[1][k] = finish_acc<OutT>(acc[1]);
+                res[2][k] = finish_acc<OutT>(swap_rb ? acc[0] : acc[2]);
+            }
+        } else
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int x = xbeg + k;
@@ -240,16 +387,16 @@ int k_crop_warp(hbp_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w,
                 int out_dtype) {
     if (P <= 0) return HBP_OK;
     if (!(ctx->attr_flags & ATTR_CROP)) {
-        HBP_CUDA(cudaFuncSetAttribute(crop_warp_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        HBP_CUDA(cudaFuncSetAttribute(crop_warp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        HBP_CUDA(cudaFuncSetAttribute(crop_warp_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2 * kSmemPad));
+        HBP_CUDA(cudaFuncSetAttribute(crop_warp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2 * kSmemPad));
         ctx->attr_flags |= ATTR_CROP;
     }
     dim3 grid((out_h + kBandRows - 1) / kBandRows, P);
     if (out_dtype == HBP_F16)
-        crop_warp_kernel<__half><<<grid, kThreads, kSmemBudget, ctx->stream>>>(
+        crop_warp_kernel<__half><<<grid, kThreads, kSmemBudget + 2 * kSmemPad, ctx->stream>>>(
             frames, n_frames, h, w, M, frame_idx, P, out_h, out_w, swap_rb, (__half*)out);
     else
-        crop_warp_kernel<float><<<grid, kThreads, kSmemBudget, ctx->stream>>>(
+        crop_warp_kernel<float><<<grid, kThreads, kSmemBudget + 2 * kSmemPad, ctx->stream>>>(
             frames, n_frames, h, w, M, frame_idx, P, out_h, out_w, swap_rb, (float*)out);
     HBP_LAUNCH_CHECK(ctx);
     return HBP_OK;

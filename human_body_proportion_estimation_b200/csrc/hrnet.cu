@@ -579,53 +579,58 @@ struct UpaddGroup { UpaddProblem p[3]; };
 
 __global__ void __launch_bounds__(256)
 upsample_add_group_kernel(const __grid_constant__ UpaddGroup g, int P) {
+    // grid-stride over the problem's blocks with a few CTAs per SM only: the launch then leaves room for the
+    // persistent conv group (last links of the stride-2 chains) that runs beside it on the other stream.
+    // 32-bit index arithmetic throughout (P*H*W*C/8 < 2^31): 64-bit div/mod dominated the old kernel.
     const UpaddProblem& q = g.p[blockIdx.y];
-    if (blockIdx.x >= q.blocks) return;
-    const int H = q.H, W = q.W, C = q.C;
-    const int c8n = C >> 3;
-    const size_t total = (size_t)P * H * W * c8n;
-    const size_t half_n = (total + 1) >> 1;
-    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i0 >= half_n) return;
-    const size_t idx[2] = {i0, i0 + half_n};
-    uint4 v[2][4];
-    bool on[2];
+    const unsigned H = q.H, W = q.W, C = q.C;
+    const unsigned c8n = C >> 3;
+    const unsigned total = (unsigned)P * H * W * c8n;
+    const unsigned half_n = (total + 1) >> 1;
+    const bool has_b = q.b != nullptr, has_c = q.c != nullptr;
+    for (unsigned blk = blockIdx.x; blk < q.blocks; blk += gridDim.x) {
+        const unsigned i0 = blk * blockDim.x + threadIdx.x;
+        if (i0 >= half_n) continue;
+        const unsigned idx[2] = {i0, i0 + half_n};
+        uint4 v[2][4];
+        bool on[2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        on[u] = idx[u] < total;
-        if (!on[u]) continue;
-        const int c8 = (int)(idx[u] % c8n);
-        const size_t pix = idx[u] / c8n;
-        const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
-        auto src = [&](const __half* s, int f) {
-            const int hs = H / f, ws = W / f;
-            return __ldg(reinterpret_cast<const uint4*>(s + (((size_t)n * hs + h / f) * ws + w / f) * C + c8 * 8));
-        };
-        v[u][0] = *reinterpret_cast<const uint4*>(q.res + pix * C + c8 * 8);
-        v[u][1] = src(q.a, q.fa);
-        if (q.b) v[u][2] = src(q.b, q.fb);
-        if (q.c) v[u][3] = src(q.c, q.fc);
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        if (!on[u]) continue;
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        auto add = [&](const uint4& t4) {
-            const __half2* hq = reinterpret_cast<const __half2*>(&t4);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { const float2 t = __half22float2(hq[k]); acc[2 * k] += t.x; acc[2 * k + 1] += t.y; }
-        };
-        add(v[u][0]); add(v[u][1]);
-        if (q.b) add(v[u][2]);
-        if (q.c) add(v[u][3]);
-        __align__(16) __half2 pk[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float x0 = acc[2 * k], x1 = acc[2 * k + 1];
-            if (q.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-            pk[k] = __floats2half2_rn(x0, x1);
+        for (int u = 0; u < 2; ++u) {
+            on[u] = idx[u] < total;
+            if (!on[u]) continue;
+            const unsigned c8 = idx[u] % c8n;
+            const unsigned pix = idx[u] / c8n;
+            const unsigned w = pix % W, hn = pix / W, h = hn % H, n = hn / H;
+            auto src = [&](const __half* s, unsigned f) {
+                const unsigned hs = H / f, ws = W / f;
+                return __ldg(reinterpret_cast<const uint4*>(s + ((size_t)(n * hs + h / f) * ws + w / f) * C + c8 * 8));
+            };
+            v[u][0] = *reinterpret_cast<const uint4*>(q.res + (size_t)idx[u] * 8);
+            v[u][1] = src(q.a, q.fa);
+            if (has_b) v[u][2] = src(q.b, q.fb);
+            if (has_c) v[u][3] = src(q.c, q.fc);
         }
-        *reinterpret_cast<uint4*>(q.out + idx[u] * 8) = *reinterpret_cast<const uint4*>(pk);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!on[u]) continue;
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            auto add = [&](const uint4& t4) {
+                const __half2* hq = reinterpret_cast<const __half2*>(&t4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float2 t = __half22float2(hq[k]); acc[2 * k] += t.x; acc[2 * k + 1] += t.y; }
+            };
+            add(v[u][0]); add(v[u][1]);
+            if (has_b) add(v[u][2]);
+            if (has_c) add(v[u][3]);
+            __align__(16) __half2 pk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float x0 = acc[2 * k], x1 = acc[2 * k + 1];
+                if (q.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                pk[k] = __floats2half2_rn(x0, x1);
+            }
+            *reinterpret_cast<uint4*>(q.out + (size_t)idx[u] * 8) = *reinterpret_cast<const uint4*>(pk);
+        }
     }
 }
 
@@ -810,6 +815,16 @@ static int ensure_batch(hbp_ctx* ctx, HrnetModel* m, int P) {
     for (int b = 0; b < m->n_bufs; ++b)
         HBP_CUDA(cudaMalloc(&m->bufs[b], m->buf_elems_per_image[b] * (size_t)cap * sizeof(__half)));
     m->cap_P = cap;
+    if (!(ctx->attr_flags & ATTR_CONV)) {
+        // The element-wise kernels run beside tensor-core CTAs that need ~200 KB of shared memory.  An SM
+        // changes its L1 / shared-memory split only when it is idle, so a streaming kernel that keeps the
+        // default (L1-heavy) split on every SM locks those CTAs out until it has finished (measured: the
+        // last stride-2 links of a fuse stage started 15-24 us late, profiles/r01_timeline_fuse_levels.md).
+        HBP_CUDA(cudaFuncSetAttribute(upsample_add_group_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        HBP_CUDA(cudaFuncSetAttribute(upsample_add_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        HBP_CUDA(cudaFuncSetAttribute(timeline_stamp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        ctx->attr_flags |= ATTR_CONV;
+    }
     m->umma.assign(m->ops.size(), nullptr);
     m->groups.assign(m->ops.size(), nullptr);
     return HBP_OK;
@@ -926,7 +941,9 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
                 q.blocks = (unsigned)((total + 255) / 256);
                 max_blocks = std::max(max_blocks, q.blocks);
             }
-            upsample_add_group_kernel<<<dim3(max_blocks, (unsigned)op.members.size()), 256, 0, st>>>(g, P);
+            static const int upadd_bpsm = getenv("HBP_UPADD_BPSM") ? atoi(getenv("HBP_UPADD_BPSM")) : 8;      // blocks per SM over all problems
+            const unsigned per_problem = (unsigned)std::max<size_t>(1, (size_t)ctx->sm_count * upadd_bpsm / op.members.size());
+            upsample_add_group_kernel<<<dim3(std::min(max_blocks, per_problem), (unsigned)op.members.size()), 256, 0, st>>>(g, P);
         } else if (op.kind == OP_GROUP) {
             // grouped launch when every member runs on the tensor engine; member by member otherwise
             bool all = m->engine == 1;

@@ -113,3 +113,20 @@ def test_host_length_helper_matches_reference_values():
         assert a == b
     with pytest.raises(UnboundLocalError):
         PoseEstimator.get_keypoint_dist_dict(0.41, k, {5}, strict=True)
+
+
+def test_crop_fp16_finalize_is_exact_for_every_accumulator():
+    """csrc/crop_warp.cu finish_acc<__half>: the bilinear blend is an integer sum acc = sum(byte * w), w in
+    1/1024 units (0 <= acc <= 255*1024).  The fp16 output is produced with ONE fp32 multiply by RN(1/261120)
+    instead of the correctly rounded fp32 quotient (acc/1024)/255 that cv2 + the reference's `/255` give;
+    exhaustively: both round to the same fp16 for every possible accumulator."""
+    acc = np.arange(0, 255 * 1024 + 1, dtype=np.int64)
+    ref32 = (acc.astype(np.float32) / np.float32(1024.0)) / np.float32(255.0)
+    y = np.float32(1.0) / np.float32(261120.0)
+    one_mul = (acc.astype(np.float64) * np.float64(y)).astype(np.float32)      # RN of the exact product = the kernel's FMA
+    assert np.array_equal(one_mul.astype(np.float16), ref32.astype(np.float16))
+    # and the fp32 path's Markstein step reproduces the correctly rounded quotient
+    q = acc.astype(np.float32) * (np.float32(1.0) / np.float32(255.0))
+    r = (acc.astype(np.float64) - q.astype(np.float64) * 255.0).astype(np.float32)
+    q2 = (q.astype(np.float64) + r.astype(np.float64) * np.float64(np.float32(1.0) / np.float32(255.0))).astype(np.float32)
+    assert np.array_equal(q2 * np.float32(2.0 ** -10), ref32)

@@ -10,6 +10,7 @@ try:
     d = json.load(open("gpurun_out/bench_$TAG.json"))
     print("value", d["value"], "e2e", d["e2e"]["value"], "hrnet_ms", d["roofline"]["hrnet_ms"], "frac", d["roofline"]["frac"])
     print(d.get("stages_ms"))
+    print({k: (round(v["frac"], 3), round(v["ms"], 3)) for k, v in d.get("stage_rooflines", {}).items()})
 except Exception as e:
     print("no bench json", e)
 PY
