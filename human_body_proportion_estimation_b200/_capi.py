@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libhbp_b200.so")
 HOST, DEVICE = 0, 1
 U8, F16, F32 = 0, 1, 2
 NCHW, NHWC = 0, 1
-PRE_COPY, PRE_STRETCH, PRE_LETTERBOX = 0, 1, 2
+PRE_COPY, PRE_STRETCH, PRE_LETTERBOX, PRE_LETTERBOX_PIL = 0, 1, 2, 3
 
 _lib = None
 

@@ -178,7 +178,7 @@ int hbp_preprocess(hbp_ctx* ctx, const uint8_t* frames, int n, int h, int w, int
                    int out_w, int swap_rb, int pad_value, void* out, int out_dtype, int out_layout, int mem) {
     BIND(ctx);
     HBP_REQUIRE(frames && out && n > 0 && h > 0 && w > 0 && out_h > 0 && out_w > 0, "bad shape");
-    HBP_REQUIRE(mode >= HBP_PRE_COPY && mode <= HBP_PRE_LETTERBOX, "bad mode");
+    HBP_REQUIRE(mode >= HBP_PRE_COPY && mode <= HBP_PRE_LETTERBOX_PIL, "bad mode");
     HBP_REQUIRE(out_dtype >= HBP_U8 && out_dtype <= HBP_F32, "bad dtype");
     HBP_REQUIRE(mode != HBP_PRE_COPY || (out_h == h && out_w == w), "COPY mode needs out size == in size");
     size_t esz = out_dtype == HBP_U8 ? 1 : out_dtype == HBP_F16 ? 2 : 4;

@@ -37,7 +37,8 @@ enum {
     SC_IN0 = 0, SC_IN1, SC_IN2, SC_IN3, SC_IN4, SC_IN5,   // host-mode input staging
     SC_OUT0, SC_OUT1, SC_OUT2, SC_OUT3, SC_OUT4, SC_OUT5, SC_OUT6,  // host-mode output staging
     SC_NMS_CAND, SC_NMS_SORTED, SC_NMS_MASK, SC_NMS_MISC,
-    SC_PIPE_CROPS, SC_PIPE_HM, SC_PIPE_MISC, SC_PIPE_FRAMES
+    SC_PIPE_CROPS, SC_PIPE_HM, SC_PIPE_MISC, SC_PIPE_FRAMES,
+    SC_PRE_COEF, SC_PRE_TMP                               // PIL-bicubic letterbox: coefficient tables, uint8 intermediate
 };
 
 void hbp_set_error(const char* fmt, ...);

@@ -7,14 +7,16 @@ import numpy as np
 
 from . import engine as _engine
 from . import onnx_utils
-from ._capi import PRE_LETTERBOX
+from ._capi import PRE_LETTERBOX, PRE_LETTERBOX_PIL
 
 
-def preprocess_image(pil_image, in_size=(640, 640), engine=None):
-    """obj_det_yolov5_onnx.py:27-36: letterbox (pad 128), HWC->CHW float32, /255."""
+def preprocess_image(pil_image, in_size=(640, 640), engine=None, resample="bicubic"):
+    """obj_det_yolov5_onnx.py:27-36: letterbox (PIL BICUBIC like the reference, pad 128), HWC->CHW
+    float32, /255.  resample="bilinear": cv2.resize-exact bilinear instead."""
     eng = engine or _engine.default_engine()
     in_w, in_h = in_size
-    return eng.preprocess(np.asarray(pil_image), PRE_LETTERBOX, in_h, in_w, False, 128, np.float32)[0]
+    mode = PRE_LETTERBOX_PIL if resample == "bicubic" else PRE_LETTERBOX
+    return eng.preprocess(np.asarray(pil_image), mode, in_h, in_w, False, 128, np.float32)[0]
 
 
 def postprocess_decoded(output, conf_thres=0.4, iou_thres=0.5, classes=None, engine=None):

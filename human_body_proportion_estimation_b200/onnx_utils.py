@@ -7,7 +7,7 @@ types), numpy otherwise.
 import numpy as np
 
 from . import engine as _engine
-from ._capi import PRE_LETTERBOX, NHWC
+from ._capi import PRE_LETTERBOX, PRE_LETTERBOX_PIL, NHWC
 
 
 def _np(x):
@@ -46,14 +46,15 @@ def w_non_max_suppression(prediction, num_classes, conf_thres=0.5, nms_thres=0.4
     return [None if o is None else _like(prediction, o) for o in out]
 
 
-def letterbox_image(image, size, engine=None):
-    """onnx_utils.py:225-235 geometry (aspect-keeping resize, centred paste on 128).
-    Takes/returns a PIL image or an (H,W,3) uint8 array.  Resampler: cv2-exact
-    bilinear (the reference's PIL BICUBIC is a later row)."""
+def letterbox_image(image, size, engine=None, resample="bicubic"):
+    """onnx_utils.py:225-235: aspect-keeping resize with PIL's antialiased BICUBIC (reproduced bit
+    for bit on the GPU), centred paste on grey 128.  Takes/returns a PIL image or an (H,W,3) uint8
+    array.  resample="bilinear" selects the cv2.resize-exact bilinear sampler instead."""
     eng = engine or _engine.default_engine()
     arr = np.asarray(image)
     w, h = size
-    out = eng.preprocess(arr, PRE_LETTERBOX, h, w, False, 128, np.uint8, NHWC)[0]
+    mode = PRE_LETTERBOX_PIL if resample == "bicubic" else PRE_LETTERBOX
+    out = eng.preprocess(arr, mode, h, w, False, 128, np.uint8, NHWC)[0]
     if not isinstance(image, np.ndarray):
         from PIL import Image
         return Image.fromarray(out)

@@ -85,14 +85,15 @@ HBP_API int hbp_kernel_launches(hbp_ctx* ctx, uint64_t* n);   /* kernels of this
  * hble/modules/pose_estimator.py:29-45 and hble/pose_est_hrnet_trtserver.py:15-19
  * (mode STRETCH: cv2.resize-exact 11-bit bilinear to out_w x out_h),
  * hble/obj_det_yolov5_onnx.py:27-36 + hble/modules/onnx_utils.py:225-235
- * (mode LETTERBOX: the reference's scale/int()/centred-paste geometry on grey
- * `pad_value`; sampler = cv2.resize bilinear, the reference's PIL bicubic is a
- * later row).
+ * (mode LETTERBOX_PIL: the reference's scale/int()/centred-paste geometry on grey
+ * `pad_value` with the reference's own resampler, PIL's antialiased BICUBIC
+ * (hble/modules/onnx_utils.py:232), reproduced bit for bit; mode LETTERBOX: same
+ * geometry with the cv2.resize bilinear sampler).
  * frames: (n,h,w,3) u8.  swap_rb!=0 reverses the channel order (BGR<->RGB).
  * out: (n,3,out_h,out_w) or (n,out_h,out_w,3); HBP_U8 keeps 0..255, HBP_F16 /
  * HBP_F32 store value/255 (correctly rounded).  In COPY mode out_h/out_w must
  * equal h/w. */
-typedef enum { HBP_PRE_COPY = 0, HBP_PRE_STRETCH = 1, HBP_PRE_LETTERBOX = 2 } hbp_pre_mode;
+typedef enum { HBP_PRE_COPY = 0, HBP_PRE_STRETCH = 1, HBP_PRE_LETTERBOX = 2, HBP_PRE_LETTERBOX_PIL = 3 } hbp_pre_mode;
 HBP_API int hbp_preprocess(hbp_ctx* ctx, const uint8_t* frames, int n, int h, int w,
                    int mode, int out_h, int out_w, int swap_rb, int pad_value,
                    void* out, int out_dtype, int out_layout, int mem);

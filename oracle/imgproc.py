@@ -183,3 +183,95 @@ def letterbox_linear(frame_rgb_u8, w=640, h=640, pad=128):
     out = np.transpose(canvas, (2, 0, 1)).astype(np.float32)
     out /= 255.0
     return out
+
+
+# ---------------------------------------------------------------------------
+# PIL (Pillow) antialiased bicubic resize -- the resampler of the reference's YOLO letterbox
+# (modules/onnx_utils.py:232, `image.resize((nw, nh), Image.BICUBIC)`; pillow==10.3.0 in
+# requirements.txt:6).  Pillow is a third-party dependency, not under /root/reference: this restates
+# its published algorithm (src/libImaging/Resample.c: precompute_coeffs, normalize_coeffs_8bpc,
+# ImagingResampleHorizontal_8bpc / Vertical_8bpc) and is pinned bit for bit against the Pillow installed
+# in this container (12.2.0; the 8-bit resample path is unchanged since 7.0) through
+# tests/golden/letterbox_pil.npz.
+# ---------------------------------------------------------------------------
+PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def _pil_bicubic_filter(x):
+    a = -0.5
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pil_bicubic_coeffs(in_size, out_size):
+    """-> (ksize, bounds[out_size,2] = (first tap, tap count), kk[out_size,ksize] int32 fixed point)."""
+    scale = filterscale = float(in_size) / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 2.0 * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        w = [_pil_bicubic_filter((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        for x in range(xmax):
+            v = w[x] / ww if ww != 0.0 else w[x]
+            kk[xx, x] = int(-0.5 + v * (1 << PIL_PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << PIL_PRECISION_BITS))
+        bounds[xx] = (xmin, xmax)
+    return ksize, bounds, kk
+
+
+def _pil_pass(img, out_size, axis):
+    """one 8-bit resample pass along `axis` (0 = vertical, 1 = horizontal) of an (H,W,C) uint8 image"""
+    src = np.moveaxis(img, axis, 0).astype(np.int64)
+    _, bounds, kk = pil_bicubic_coeffs(src.shape[0], out_size)
+    out = np.empty((out_size,) + src.shape[1:], np.uint8)
+    for xx in range(out_size):
+        lo, n = bounds[xx]
+        acc = np.tensordot(kk[xx, :n].astype(np.int64), src[lo:lo + n], axes=(0, 0)) + (1 << (PIL_PRECISION_BITS - 1))
+        out[xx] = np.clip(acc >> PIL_PRECISION_BITS, 0, 255)
+    return np.moveaxis(out, 0, axis)
+
+
+def resize_bicubic_pil(img_u8, w, h):
+    """PIL.Image.resize((w, h), BICUBIC) of an (H,W,3) uint8 array: horizontal pass into a uint8
+    intermediate, then the vertical pass (Resample.c ImagingResampleInner)."""
+    ih, iw = img_u8.shape[:2]
+    out = img_u8
+    if w != iw:
+        out = _pil_pass(out, w, 1)
+    if h != ih:
+        out = _pil_pass(out, h, 0)
+    return np.ascontiguousarray(out)
+
+
+def letterbox_pil(frame_rgb_u8, w=640, h=640, pad=128):
+    """The reference's letterbox + preprocess (modules/onnx_utils.py:225-235,
+    obj_det_yolov5_onnx.py:27-36): PIL-bicubic resize to int(iw*scale) x int(ih*scale), centred
+    paste on grey 128, CHW float32 / 255."""
+    ih, iw = frame_rgb_u8.shape[:2]
+    scale = min(w / iw, h / ih)
+    nw, nh = int(iw * scale), int(ih * scale)
+    canvas = np.full((h, w, 3), pad, np.uint8)
+    ox, oy = (w - nw) // 2, (h - nh) // 2
+    canvas[oy:oy + nh, ox:ox + nw] = resize_bicubic_pil(frame_rgb_u8, nw, nh)
+    out = np.transpose(canvas, (2, 0, 1)).astype(np.float32)
+    out /= 255.0
+    return out

@@ -243,11 +243,36 @@ def gen_misc():
                         letterbox_pad=lb[0, 0])
 
 
+def gen_letterbox_pil():
+    """reference modules/onnx_utils.py:225-235 letterbox_image (PIL BICUBIC, antialiased) executed as is."""
+    import hashlib
+    from PIL import Image
+    import PIL
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from human_body_proportion_estimation_b200 import synth
+    rng = np.random.default_rng(77)
+    out = {"pil_version": np.array(PIL.__version__)}
+    cases = [((97, 131), (64, 48)), ((20, 30), (64, 64)), ((108, 192), (64, 64)), ((64, 64), (64, 64)), ((33, 250), (96, 40))]
+    for i, ((ih, iw), (w, h)) in enumerate(cases):
+        img = rng.integers(0, 256, (ih, iw, 3), dtype=np.uint8)
+        lb = np.asarray(ou.letterbox_image(Image.fromarray(img), (w, h)))
+        out["img%d" % i] = img
+        out["size%d" % i] = np.array([w, h])
+        out["lb%d" % i] = lb
+    # config 3: the synthetic 1080p frame (white noise = worst case for a resampler) -> 640 x 640
+    frame = synth.frame_u8(smooth=False)
+    lb = np.asarray(ou.letterbox_image(Image.fromarray(frame), (640, 640)))
+    out["lb1080_sha256"] = np.array(hashlib.sha256(lb.tobytes()).hexdigest())
+    out["lb1080_sample"] = lb[::8, ::8].copy()
+    np.savez_compressed(os.path.join(HERE, "letterbox_pil.npz"), **out)
+
+
 if __name__ == "__main__":
     gen_decode()
     gen_nms()
     gen_crop()
     gen_misc()
+    gen_letterbox_pil()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -172,6 +172,34 @@ def test_preprocess(eng, golden):
     assert np.array_equal(lb16[1], lb.astype(np.float16))
 
 
+def test_letterbox_pil_bicubic(eng, golden):
+    """A2 with the reference's own resampler: letterbox_image (PIL BICUBIC, onnx_utils.py:225-235) executed
+    by the reference -> golden; the CUDA two-pass kernel reproduces it bit for bit (u8), and the f32/f16
+    CHW /255 form obj_det_yolov5_onnx.py:27-36 feeds the detector."""
+    import hashlib
+    from human_body_proportion_estimation_b200._capi import NHWC, PRE_LETTERBOX_PIL
+    from human_body_proportion_estimation_b200 import obj_det_yolov5, onnx_utils
+    from oracle import imgproc
+    g = golden("letterbox_pil.npz")
+    i = 0
+    while "img%d" % i in g:
+        w, h = (int(v) for v in g["size%d" % i])
+        got = eng.preprocess(g["img%d" % i], PRE_LETTERBOX_PIL, h, w, False, 128, np.uint8, NHWC)[0]
+        assert np.array_equal(got, g["lb%d" % i]), i
+        i += 1
+    frame = synth.frame_u8(smooth=False)                       # config 3's 1080p frame, white noise
+    u8 = onnx_utils.letterbox_image(frame, (640, 640), engine=eng)
+    assert np.array_equal(u8[::8, ::8], g["lb1080_sample"])
+    assert hashlib.sha256(np.ascontiguousarray(u8).tobytes()).hexdigest() == str(g["lb1080_sha256"])
+    chw = obj_det_yolov5.preprocess_image(frame, (640, 640), engine=eng)
+    assert np.array_equal(chw, imgproc.letterbox_pil(frame, 640, 640))
+    # batch of two 4K frames, fp16 NCHW with the BGR->RGB swap
+    big = synth.frame_u8(2160, 3840, seed=9, smooth=False)
+    two = eng.preprocess(np.stack([big, big[::-1]]), PRE_LETTERBOX_PIL, 640, 640, True, 128, np.float16)
+    assert np.array_equal(two[0], imgproc.letterbox_pil(big[..., ::-1], 640, 640).astype(np.float16))
+    assert np.array_equal(two[1], imgproc.letterbox_pil(big[::-1, :, ::-1], 640, 640).astype(np.float16))
+
+
 def unpack(arr, cnt):
     return [None if c < 0 else arr[i, :c] for i, c in enumerate(cnt)]
 

@@ -185,3 +185,25 @@ def test_oracle_vs_live_reference():
     t = torch.from_numpy(dec.copy())
     ref = ou.non_max_suppression(t, 0.4, 0.5)[0].numpy()
     assert np.array_equal(detect.official_nms(dec, 0.4, 0.5)[0], ref)
+
+
+def test_letterbox_pil_bicubic(golden):
+    """A2: the reference's letterbox_image (PIL BICUBIC, antialiased; onnx_utils.py:225-235) run as is ->
+    the oracle's restatement of Pillow's 8-bit resample reproduces it bit for bit."""
+    import hashlib
+    from oracle import imgproc
+    from human_body_proportion_estimation_b200 import synth
+    g = golden("letterbox_pil.npz")
+    i = 0
+    while "img%d" % i in g:
+        w, h = (int(v) for v in g["size%d" % i])
+        got = imgproc.letterbox_pil(g["img%d" % i], w, h)
+        want = np.transpose(g["lb%d" % i], (2, 0, 1)).astype(np.float32) / np.float32(255.0)
+        assert np.array_equal(got, want), i
+        i += 1
+    assert i >= 5
+    frame = synth.frame_u8(smooth=False)
+    lb = imgproc.letterbox_pil(frame, 640, 640)
+    u8 = np.ascontiguousarray(np.transpose(np.rint(lb * 255.0), (1, 2, 0)).astype(np.uint8))
+    assert np.array_equal(u8[::8, ::8], g["lb1080_sample"])
+    assert hashlib.sha256(u8.tobytes()).hexdigest() == str(g["lb1080_sha256"])
