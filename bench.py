@@ -193,7 +193,7 @@ def config_dict():
 def stage_rooflines(eng, hbm_gbs):
     import ctypes as C
     from human_body_proportion_estimation_b200 import geometry, synth
-    from human_body_proportion_estimation_b200._capi import DEVICE, F16, NCHW, NHWC, PRE_COPY, PRE_LETTERBOX, U8, check
+    from human_body_proportion_estimation_b200._capi import DEVICE, F16, NCHW, NHWC, PRE_COPY, PRE_LETTERBOX, PRE_LETTERBOX_PIL, U8, check
     from human_body_proportion_estimation_b200.engine import KEYPOINT_THRES_LIST
     lib, ctx = eng._lib, eng._ctx
     out = {}
@@ -229,6 +229,10 @@ def stage_rooflines(eng, hbm_gbs):
                                                 C.c_void_p(d_lb), F16, NCHW, DEVICE)))
     entry("k1_letterbox_64x4k_to_640_f16", nf * (frame.nbytes + 3 * 640 * 640 * 2), ms,
           "64 frames 2160x3840x3 u8 -> 3x640x640 f16, one launch (bytes = whole frame + output)")
+    ms = timed(lambda: check(lib.hbp_preprocess(ctx, C.c_void_p(d_frames), nf, fh, fw, PRE_LETTERBOX_PIL, 640, 640, 1, 128,
+                                                C.c_void_p(d_lb), F16, NCHW, DEVICE)))
+    entry("k1_letterbox_pil_bicubic_64x4k_to_640_f16", nf * (frame.nbytes + 3 * 640 * 640 * 2), ms,
+          "64 frames 2160x3840x3 u8 -> 3x640x640 f16 with PIL's antialiased bicubic (two passes, u8 intermediate), bytes = whole frame + output")
     eng.dev_free(d_copy); eng.dev_free(d_lb)
 
     # K4: 4096 crops (64 per frame) from the 64 4K frames -> (4096,3,256,192) f16
@@ -271,7 +275,7 @@ def run_ours(args, rank, world, local_rank):
     import ctypes as C
     from human_body_proportion_estimation_b200 import _capi, hrnet_arch, synth
     from human_body_proportion_estimation_b200.engine import Engine, KEYPOINT_THRES_LIST
-    from human_body_proportion_estimation_b200._capi import DEVICE, F16, F32, NCHW, PRE_LETTERBOX, check, ptr
+    from human_body_proportion_estimation_b200._capi import DEVICE, F16, F32, NCHW, PRE_LETTERBOX, PRE_LETTERBOX_PIL, check, ptr
 
     from human_body_proportion_estimation_b200 import dist_util
     if world > 1:
@@ -384,6 +388,8 @@ def run_ours(args, rank, world, local_rank):
 
         stages["letterbox_1080p_to_640_f16"] = timed(lambda: check(lib.hbp_preprocess(
             ctx, C.c_void_p(d_frame), 1, FRAME_H, FRAME_W, PRE_LETTERBOX, 640, 640, 1, 128, C.c_void_p(d_lb), F16, NCHW, DEVICE)))
+        stages["letterbox_pil_bicubic_1080p_to_640_f16"] = timed(lambda: check(lib.hbp_preprocess(
+            ctx, C.c_void_p(d_frame), 1, FRAME_H, FRAME_W, PRE_LETTERBOX_PIL, 640, 640, 1, 128, C.c_void_p(d_lb), F16, NCHW, DEVICE)))
         stages["yolo_nms_25200x85_person"] = timed(lambda: check(lib.hbp_yolo_nms(
             ctx, C.c_void_p(d_pred), 1, 25200, 80, 0.4, 0.5, C.c_void_p(d_cls), 1, 300, C.c_void_p(d_det), C.c_void_p(d_cnt), DEVICE)))
         stages["crop_64x256x192_f16"] = timed(lambda: check(lib.hbp_crop_warp(
@@ -428,7 +434,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "p50_frame_latency_ms": statistics.median(lat), "api": "Engine.pose_pipeline (hbp_pose_pipeline)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "HRNet conv stack: %d launches per step (conv_umma_halo_kernel + conv_umma_kernel = 291, upsample_add, stem, head), one CUDA graph" % n_conv_launch,
+        "roofline": {"bound": "tensor", "kernel": "HRNet conv stack: %d launches per step (conv_umma_halo_kernel, conv_umma_pgroup_kernel (one per fuse level), conv_umma_kernel, upsample_add_group, stem, head), one CUDA graph" % n_conv_launch,
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                      "peak_source": pk["src"], "traffic": None,
                      "flop_per_launch_avg": flops_crop * P / n_conv_launch,
