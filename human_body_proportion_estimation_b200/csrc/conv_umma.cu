@@ -1208,6 +1208,7 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     // is ~ rounds * m * (MMA time of one M-tile) / (share of useful MMA rows is already inside
     // `items`): pick the (tile, N split) with the fewest M-tile rounds; ties go to the larger N
     // tile (fewer shared-memory bytes per MAC), then to the larger M (weights reused).
+    const double l2_bpc = (double)env_int("HBP_HALO_L2BPC", 64);      // L2 -> shared memory bytes per clock and SM the cost model assumes
     struct Cand { int tn, th, m, n_tile; long items; double cost; };
     Cand best{0, 0, 0, 0, 0, 1e30};
     for (int mt = 1; mt <= 2; ++mt)
@@ -1231,9 +1232,9 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
                     const double w_bytes = (double)ksz * ksz * op.cin * c * 2;
                     const double a_bytes = (double)(16 * mt + ksz - 1) * hw * op.cin * 2;      // one tile's input box
                     const bool fits = w_bytes + 2.0 * a_bytes < 190e3;
-                    const double w_cyc = (fits ? 1.0 : (double)rounds) * w_bytes / 24.0;
+                    const double w_cyc = (fits ? 1.0 : (double)rounds) * w_bytes / l2_bpc;
                     // the tile's input box is fetched once per output-channel split: it bounds the 1x1 layers
-                    const double a_cyc = (double)rounds * a_bytes / 24.0;
+                    const double a_cyc = (double)rounds * a_bytes / l2_bpc;
                     const double cost = std::max(std::max(mma_cyc, w_cyc), a_cyc);
                     const bool better = cost < best.cost * 0.97 ||
                                         (cost < best.cost * 1.03 && (c > best.n_tile || (c == best.n_tile && mt > best.m)));
@@ -1369,6 +1370,7 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
 
 int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPlan** out, bool for_group) {
     const HOp& op = m.ops[op_index];
+    const bool persistent_tiling = for_group || op.persist || (env_int("HBP_PERSIST0", 2) > 1 && op.sm_share > 0.f);
     const HTensor& ti = m.tensors[op.in];
     const int Ho = ti.h / op.stride, Wo = ti.w / op.stride;
     UmmaPlan* pl = new UmmaPlan();
@@ -1403,20 +1405,20 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     if (!n_tile) { delete pl; hbp_set_error("no N tile for Cout=%d", op.cout); return HBP_ERR_INVALID; }
     // 1x1 convolutions are epilogue-bound (K is one or a few chunks): keep the accumulator at
     // <= 128 TMEM columns so that four CTAs share an SM and overlap each other's epilogues
-    if (op.k == 1 && !for_group) while (n_tile > 128 && n_tile % 32 == 0) n_tile /= 2;
+    if (op.k == 1 && !persistent_tiling) while (n_tile > 128 && n_tile % 32 == 0) n_tile /= 2;
     // members of a persistent group share one ring of equal slots: every member's stage (A box + weight box)
     // stays <= 24 KB so that eight of them are in flight (the loads are L2-latency bound)
-    if (for_group) {
-        const int cap_n = op.cin == 32 ? 128 : 64;
+    if (persistent_tiling) {
+        const int cap_n = op.cin == 64 ? 64 : 128;             // Cin >= 128: 16 KB A + 16 KB weights per stage, six stages
         while (n_tile > cap_n && n_tile % 32 == 0) n_tile /= 2;
     }
     // M tiles per CTA: 2 when that still leaves >= 2 CTAs per SM and TMEM stays <= 256 columns
     int m_tiles = 2, tn = 0, th = 0, tw = 0;
     {
-        bool ok2 = pick_tile(Ho, Wo, 2, &tn, &th, &tw) && 2 * n_tile <= ((op.k == 1 && !for_group) ? 128 : 256) &&
-                   !(for_group && op.cin != 32);
+        bool ok2 = pick_tile(Ho, Wo, 2, &tn, &th, &tw) && 2 * n_tile <= ((op.k == 1 && !persistent_tiling) ? 128 : 256) &&
+                   !(persistent_tiling && op.cin != 32);
         // (persistent walkers want few, large work items: no minimum CTA count, no extra N split)
-        if (ok2 && !for_group) {
+        if (ok2 && !persistent_tiling) {
             const long ctas = (long)((capP + tn - 1) / tn) * (Ho / th) * (Wo / tw) * (op.cout / n_tile);
             if (ctas < 2L * ctx->sm_count) ok2 = false;
         }
@@ -1425,7 +1427,7 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     // too few CTAs: split N further (down to 32)
     {
         long ctas = (long)((capP + tn - 1) / tn) * (Ho / th) * (Wo / tw) * (op.cout / n_tile);
-        while (!for_group && ctas < ctx->sm_count && n_tile % 32 == 0 && n_tile > 32) { n_tile /= 2; ctas *= 2; }
+        while (!persistent_tiling && ctas < ctx->sm_count && n_tile % 32 == 0 && n_tile > 32) { n_tile /= 2; ctas *= 2; }
     }
     p.Ho = Ho; p.Wo = Wo; p.Cout = op.cout; p.up = op.up; p.relu = op.relu;
     p.tn = tn; p.th = th; p.tw = tw; p.m_tiles = m_tiles; p.n_tile = n_tile;
@@ -1643,9 +1645,9 @@ int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, 
             return HBP_OK;
         }
     }
-    static const int persist0 = env_int("HBP_PERSIST0", 1);
+    static const int persist0 = env_int("HBP_PERSIST0", 2);      // 1: only ops flagged `persist`; 2: also branch convs without a halo plan (256-channel 8x6 branch)
     if (p.mode == 1) launch_halo(grid, pl->smem_bytes, st, pl, p);
-    else if (persist0 && m.ops[op_index].persist && p.m_tiles * p.n_tile <= 256) {
+    else if (persist0 && (m.ops[op_index].persist || (persist0 > 1 && m.ops[op_index].sm_share > 0.f)) && p.m_tiles * p.n_tile <= 256) {
         // per-tap convolutions (stride 2, fused upsample) walk their tiles with persistent CTAs: a group of one
         const int member = op_index;
         return group_launch(ctx, m, op_index, &member, 1, P, st);
