@@ -72,6 +72,8 @@ _SIGS = {
                                     _P, _P, _I]),
     "hbp_pose_pipeline": (_I, [_P, C.POINTER(PipelineParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                _P, _P]),
+    "hbp_pose_pipeline_submit": (_I, [_P, C.POINTER(PipelineParams), _P, _P, _P, _P, _P, _P, C.POINTER(_I)]),
+    "hbp_pose_pipeline_collect": (_I, [_P, _I, _P, _P, _P, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)
 

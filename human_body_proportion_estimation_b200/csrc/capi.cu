@@ -109,6 +109,15 @@ int hbp_ctx_destroy(hbp_ctx* ctx) {
     for (int i = 0; i < HBP_SCRATCH_SLOTS; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->l2_flush) cudaFree(ctx->l2_flush);
+    for (hbp_pipe_slot& sl : ctx->pipe) {
+        if (sl.d_frames) cudaFree(sl.d_frames);
+        if (sl.d_misc) cudaFree(sl.d_misc);
+        if (sl.h_pin) cudaFreeHost(sl.h_pin);
+        if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+        if (sl.ev_crop) cudaEventDestroy(sl.ev_crop);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < HBP_TIMER_SLOTS; ++i) { cudaEventDestroy(ctx->ev_start[i]); cudaEventDestroy(ctx->ev_stop[i]); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -485,6 +494,114 @@ int hbp_pose_pipeline(hbp_ctx* ctx, const hbp_pipeline_params* prm, const uint8_
     if (scores) memcpy(scores, h_res + r_s, (size_t)P * J * 4);
     if (lengths_cm) memcpy(lengths_cm, h_res + r_l, (size_t)P * 44);
     if (ignored) memcpy(ignored, h_res + r_i, (size_t)P * 4);
+    return HBP_OK;
+}
+
+// ---- asynchronous form: two frame batches in flight --------------------------------------------
+// submit(n+1) may be called before collect(n): the host->device copy of batch n+1 runs on its own
+// stream while batch n is in the HRNet, so the PCIe transfer of the frames (6.2 MB for one 1080p
+// frame, ~5 % of a step) leaves the critical path.  Frames, parameters and results are double
+// buffered; crops and heatmaps are not (the compute stream serialises the batches).
+static int pipe_reserve(uint8_t** p, size_t* cap, size_t bytes, bool pinned) {
+    if (bytes <= *cap) return HBP_OK;
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
+    const size_t n = bytes + bytes / 4 + 256;
+    cudaError_t e = pinned ? cudaMallocHost((void**)p, n) : cudaMalloc((void**)p, n);
+    if (e != cudaSuccess) return hbp_cuda_fail(e, "pipeline slot allocation", __FILE__, __LINE__);
+    *cap = n;
+    return HBP_OK;
+}
+
+int hbp_pose_pipeline_submit(hbp_ctx* ctx, const hbp_pipeline_params* prm, const uint8_t* frames,
+                             const double* M, const int* frame_idx, const float* boxes,
+                             const double* height_cm, const float* joint_thr, int* ticket) {
+    BIND(ctx);
+    HBP_REQUIRE(prm && frames && M && frame_idx && boxes && height_cm && joint_thr && ticket, "null argument");
+    if (!ctx->hrnet) { hbp_set_error("hbp_pose_pipeline_submit before hbp_hrnet_load"); return HBP_ERR_STATE; }
+    const int P = prm->P;
+    HBP_REQUIRE(P > 0 && prm->n_frames > 0 && prm->h > 0 && prm->w > 0, "bad shape");
+    for (int p = 0; p < P; ++p)
+        HBP_REQUIRE(frame_idx[p] >= 0 && frame_idx[p] < prm->n_frames, "frame_idx out of range");
+    const int k = (int)(ctx->pipe_seq % HBP_PIPE_SLOTS);
+    hbp_pipe_slot& sl = ctx->pipe[k];
+    if (sl.busy) { hbp_set_error("pipeline slot %d has not been collected (at most %d batches in flight)", k, HBP_PIPE_SLOTS); return HBP_ERR_STATE; }
+    if (!ctx->copy_stream) HBP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!sl.ev_h2d) {
+        HBP_CUDA(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
+        HBP_CUDA(cudaEventCreateWithFlags(&sl.ev_crop, cudaEventDisableTiming));
+        HBP_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    }
+    int ih, iw, wd;
+    hrnet_dims(ctx, &ih, &iw, &wd);
+    const int Hh = ih / 4, Wh = iw / 4, J = 17;
+    const size_t frame_bytes = (size_t)prm->n_frames * prm->h * prm->w * 3;
+    const size_t o_M = 0, o_h = o_M + (size_t)P * 6 * 8, o_b = o_h + (size_t)P * 8,
+                 o_t = o_b + (size_t)P * 16, o_f = o_t + 32 * 4, par_bytes = o_f + (size_t)P * 4;
+    const size_t r_to = 0, r_k = r_to + (size_t)P * 8, r_s = r_k + (size_t)P * J * 2 * 4,
+                 r_l = r_s + (size_t)P * J * 4, r_i = r_l + (size_t)P * 11 * 4, res_bytes = r_i + (size_t)P * 4;
+    const size_t par_pad = (par_bytes + 63) & ~size_t(63);
+    // (re)allocation only while nothing of this slot is in flight: its previous batch was collected
+    if (frame_bytes > sl.frames_cap || par_pad + res_bytes > sl.misc_cap) HBP_CUDA(cudaDeviceSynchronize());
+    int st = pipe_reserve(&sl.d_frames, &sl.frames_cap, frame_bytes, false);
+    if (!st) st = pipe_reserve(&sl.d_misc, &sl.misc_cap, par_pad + res_bytes, false);
+    if (!st) st = pipe_reserve(&sl.h_pin, &sl.pin_cap, par_pad + res_bytes, true);
+    if (st) return st;
+    __half* d_crops = (__half*)hbp_scratch(ctx, SC_PIPE_CROPS, (size_t)P * 3 * ih * iw * 2);
+    void* d_hm = hbp_scratch(ctx, SC_PIPE_HM, (size_t)P * J * Hh * Wh * 2);
+    if (!d_crops || !d_hm) return HBP_ERR_NOMEM;
+    uint8_t* d_par = sl.d_misc;
+    uint8_t* d_res = sl.d_misc + par_pad;
+    uint8_t* h_par = sl.h_pin;
+    uint8_t* h_res = sl.h_pin + par_pad;
+    memcpy(h_par + o_M, M, (size_t)P * 48);
+    memcpy(h_par + o_h, height_cm, (size_t)P * 8);
+    memcpy(h_par + o_b, boxes, (size_t)P * 16);
+    memcpy(h_par + o_t, joint_thr, 17 * 4);
+    memcpy(h_par + o_f, frame_idx, (size_t)P * 4);
+    // copy stream: the slot's frame buffer is free once the crop kernel of its previous batch has read it
+    if (sl.crop_recorded) HBP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, sl.ev_crop, 0));
+    HBP_CUDA(cudaMemcpyAsync(sl.d_frames, frames, frame_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    HBP_CUDA(cudaMemcpyAsync(d_par, h_par, par_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    HBP_CUDA(cudaEventRecord(sl.ev_h2d, ctx->copy_stream));
+    // compute stream
+    HBP_CUDA(cudaStreamWaitEvent(ctx->stream, sl.ev_h2d, 0));
+    int s = k_crop_warp(ctx, sl.d_frames, prm->n_frames, prm->h, prm->w, (const double*)(d_par + o_M),
+                        (const int*)(d_par + o_f), P, ih, iw, prm->swap_rb, d_crops, HBP_F16);
+    if (s) return s;
+    HBP_CUDA(cudaEventRecord(sl.ev_crop, ctx->stream));
+    sl.crop_recorded = true;
+    s = hrnet_forward(ctx, d_crops, P, d_hm, HBP_F16);
+    if (s) return s;
+    s = k_decode_proportions(ctx, d_hm, HBP_F16, P, J, Hh, Wh, (const float*)(d_par + o_b),
+                             (const double*)(d_par + o_h), (const float*)(d_par + o_t),
+                             prm->quarter_offset, nullptr, (float*)(d_res + r_k), (float*)(d_res + r_s),
+                             nullptr, (uint32_t*)(d_res + r_i), (float*)(d_res + r_l), (double*)(d_res + r_to));
+    if (s) return s;
+    HBP_CUDA(cudaMemcpyAsync(h_res, d_res, res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    HBP_CUDA(cudaEventRecord(sl.ev_done, ctx->stream));
+    sl.busy = true; sl.P = P; sl.par_bytes = par_pad; sl.res_bytes = res_bytes;
+    *ticket = k;
+    ctx->pipe_seq++;
+    return HBP_OK;
+}
+
+int hbp_pose_pipeline_collect(hbp_ctx* ctx, int ticket, float* kpts_img, float* scores, uint32_t* ignored,
+                              float* lengths_cm, double* torso_cm) {
+    BIND(ctx);
+    HBP_REQUIRE(ticket >= 0 && ticket < HBP_PIPE_SLOTS, "bad ticket");
+    hbp_pipe_slot& sl = ctx->pipe[ticket];
+    if (!sl.busy) { hbp_set_error("ticket %d has nothing in flight", ticket); return HBP_ERR_STATE; }
+    HBP_CUDA(cudaEventSynchronize(sl.ev_done));
+    const int P = sl.P, J = 17;
+    const size_t r_to = 0, r_k = r_to + (size_t)P * 8, r_s = r_k + (size_t)P * J * 2 * 4,
+                 r_l = r_s + (size_t)P * J * 4, r_i = r_l + (size_t)P * 11 * 4;
+    const uint8_t* h_res = sl.h_pin + sl.par_bytes;
+    if (torso_cm) memcpy(torso_cm, h_res + r_to, (size_t)P * 8);
+    if (kpts_img) memcpy(kpts_img, h_res + r_k, (size_t)P * J * 8);
+    if (scores) memcpy(scores, h_res + r_s, (size_t)P * J * 4);
+    if (lengths_cm) memcpy(lengths_cm, h_res + r_l, (size_t)P * 44);
+    if (ignored) memcpy(ignored, h_res + r_i, (size_t)P * 4);
+    sl.busy = false;
     return HBP_OK;
 }
 

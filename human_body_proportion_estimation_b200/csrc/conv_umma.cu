@@ -76,13 +76,17 @@ struct ConvParams {
     uint32_t r_chunk_bytes, r_box_bytes, r_row_bytes;
     int issuers;                 // halo mode: MMA-issuing warps
     int teams;                   // halo mode: epilogue teams (2 needs an even number of ring stages and accumulator buffers) (2: alternate tiles, one accumulator buffer each)
+    int phase_maps;              // stride-2 per-tap mode: the four (row, column) parity planes of the input have their own dense tensor maps
     int dbg_flags;               // bring-up experiments: 1 = skip the output stores, 2 = skip the bias loads
     long long* dbg;              // optional phase timestamps (8 per CTA, first 64 CTAs), bring-up only
     unsigned long long* tl;      // optional [start, end] globaltimer stamps of this launch (HBP_TIMELINE)
 };
 
+struct PhaseMaps { CUtensorMap m[4]; };     // [row parity * 2 + column parity]
+
 struct UmmaPlan {
     CUtensorMap tmA, tmB, tmR;   // tmR: residual tensor (halo mode with res_smem)
+    PhaseMaps tmP;               // stride-2 per-tap convs (prm.phase_maps)
     ConvParams prm;
     size_t smem_bytes;
     int n_splits;
@@ -214,7 +218,7 @@ constexpr int kThreads = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2
 
 // One output tile of one convolution (mode 0: one TMA box per tap).  Shared by the single-conv
 // kernel and the grouped kernel below; `bx` / `by` are the tile / output-channel-split indices.
-__device__ __forceinline__ void conv_umma_body(const CUtensorMap* tmAp, const CUtensorMap* tmBp, const ConvParams& p,
+__device__ __forceinline__ void conv_umma_body(const CUtensorMap* tmAp, const CUtensorMap* tmBp, const CUtensorMap* tmPp, const ConvParams& p,
                                                const int bx, const int by, uint8_t* smem_raw) {
     // carve: [A stages][B stages] (1024-aligned), then barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -273,8 +277,12 @@ __device__ __forceinline__ void conv_umma_body(const CUtensorMap* tmAp, const CU
                 mbar_wait(empty_bar + 8u * s, ph ^ 1u);
                 if (elect_one()) {
                     mbar_expect_tx(full_bar + 8u * s, p.tx_bytes);
-                    tma_load_4d(a_base + s * p.a_stage_bytes, tmAp, full_bar + 8u * s,
-                                cc * p.chunk, w0 * p.stride + dx, h0 * p.stride + dy, n0);
+                    if (p.phase_maps)          // tap (dy,dx) of a stride-2 conv = a dense box of one parity plane (see umma_plan_create)
+                        tma_load_4d(a_base + s * p.a_stage_bytes, tmPp + ((dy & 1) * 2 + (dx & 1)), full_bar + 8u * s,
+                                    cc * p.chunk, w0 - (dx < 0), h0 - (dy < 0), n0);
+                    else
+                        tma_load_4d(a_base + s * p.a_stage_bytes, tmAp, full_bar + 8u * s,
+                                    cc * p.chunk, w0 * p.stride + dx, h0 * p.stride + dy, n0);
                     tma_load_2d(b_base + s * p.b_stage_bytes, tmBp, full_bar + 8u * s,
                                 cc * p.chunk, tap * p.Cout + n_off);
                 }
@@ -403,9 +411,9 @@ __device__ __forceinline__ void conv_umma_body(const CUtensorMap* tmAp, const CU
 
 __global__ void __launch_bounds__(kThreads)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const ConvParams p) {
+                 const __grid_constant__ PhaseMaps tmP, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    conv_umma_body(&tmA, &tmB, p, (int)blockIdx.x, (int)blockIdx.y, smem_raw);
+    conv_umma_body(&tmA, &tmB, &tmP.m[0], p, (int)blockIdx.x, (int)blockIdx.y, smem_raw);
 }
 
 // Persistent grouped launch (mode 0: one TMA box per tap).  A group is a list of independent
@@ -420,6 +428,7 @@ constexpr int kMaxGroup = 16;
 constexpr int kMaxPStages = 12;
 struct alignas(64) GroupEntry {
     CUtensorMap tmA, tmB;
+    PhaseMaps tmP;
     ConvParams p;
     int gx, gy;
 };
@@ -507,6 +516,7 @@ conv_umma_pgroup_kernel(const GroupEntry* __restrict__ table, const __grid_const
             const int n_off = by * p.n_tile;
             const int ksz = p.ksz, pad = ksz / 2, taps = ksz * ksz, n_chunks = p.n_chunks, chunk = p.chunk, stride = p.stride, Cout = p.Cout;
             const uint32_t tx = p.tx_bytes, a_bytes = p.a_stage_bytes;
+            const bool phase = p.phase_maps != 0;
             if (p.tl && lane == 0) atomicMin(p.tl, globaltimer_ns());
             for (int tap = 0; tap < taps; ++tap) {
                 const int dy = tap / ksz - pad, dx = tap % ksz - pad;
@@ -514,7 +524,11 @@ conv_umma_pgroup_kernel(const GroupEntry* __restrict__ table, const __grid_const
                     mbar_wait(empty_bar + 8u * s, ph ^ 1u);
                     if (elect_one()) {
                         mbar_expect_tx(full_bar + 8u * s, tx);
-                        tma_load_4d(ring + s * slot, tmA, full_bar + 8u * s, cc * chunk, w0 * stride + dx, h0 * stride + dy, n0);
+                        if (phase)
+                            tma_load_4d(ring + s * slot, &table[e].tmP.m[(dy & 1) * 2 + (dx & 1)], full_bar + 8u * s, cc * chunk,
+                                        w0 - (dx < 0), h0 - (dy < 0), n0);
+                        else
+                            tma_load_4d(ring + s * slot, tmA, full_bar + 8u * s, cc * chunk, w0 * stride + dx, h0 * stride + dy, n0);
                         tma_load_2d(ring + s * slot + a_bytes, tmB, full_bar + 8u * s, cc * chunk, tap * Cout + n_off);
                     }
                     __syncwarp();
@@ -1477,6 +1491,32 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
             return HBP_ERR_CUDA;
         }
     }
+    for (int q = 0; q < 4; ++q) pl->tmP.m[q] = pl->tmA;          // placeholders unless phase maps are in use
+    if (op.stride == 2 && env_int("HBP_S2_PHASE", 1) && ti.h % 2 == 0 && ti.w % 2 == 0) {
+        // Stride-2 taps as DENSE boxes.  Input pixel (2y+dy, 2x+dx) lies in the parity plane (dy&1, dx&1) of the
+        // input at plane coordinates (y - (dy<0), x - (dx<0)); a parity plane is the tensor
+        // (C, W/2, H/2, N) with strides (2C, 2WC, HWC) based at pixel (py, px).  A tiled map with
+        // elementStrides = 2 walks the whole 2tw x 2th span of the box and keeps a quarter of it
+        // (27 B/clk/SM measured on the stem's conv2); the plane view fetches only the rows it delivers.
+        // Out-of-range plane coordinates (-1) are exactly the convolution's zero padding.
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                cuuint64_t gdim[4] = {(cuuint64_t)ti.c, (cuuint64_t)(ti.w / 2), (cuuint64_t)(ti.h / 2), (cuuint64_t)capP};
+                cuuint64_t gstr[3] = {(cuuint64_t)ti.c * 4, (cuuint64_t)ti.w * ti.c * 4, (cuuint64_t)ti.h * ti.w * ti.c * 2};
+                cuuint32_t box[4] = {(cuuint32_t)p.chunk, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+                cuuint32_t est[4] = {1, 1, 1, 1};
+                CUresult r = enc(&pl->tmP.m[py * 2 + px], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                                 m.bufs[ti.buf] + ((size_t)py * ti.w + px) * ti.c, gdim, gstr, box, est,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) {
+                    delete pl;
+                    hbp_set_error("cuTensorMapEncodeTiled(A parity plane) failed (%d) for %s", (int)r, op.name.c_str());
+                    return HBP_ERR_CUDA;
+                }
+            }
+        p.phase_maps = 1;
+    }
     {
         int st = encode_weights_map(enc, pl, m, op, p.chunk, n_tile, sw);
         if (st) { delete pl; return st; }
@@ -1525,7 +1565,7 @@ static int group_launch(hbp_ctx* ctx, HrnetModel& m, int slot_index, const int* 
             const UmmaPlan* pl = m.umma[oi];
             if (!pl || pl->prm.mode != 0) { hbp_set_error("group member %s has no mode-0 plan", m.ops[oi].name.c_str()); return HBP_ERR_STATE; }
             GroupEntry& e = g->h[i];
-            e.tmA = pl->tmA; e.tmB = pl->tmB; e.p = pl->prm;
+            e.tmA = pl->tmA; e.tmB = pl->tmB; e.tmP = pl->tmP; e.p = pl->prm;
             e.p.P = P;
             e.p.tl = m.d_timeline ? m.d_timeline + 2 * oi : nullptr;
             const int tiles_n = (P + e.p.tn - 1) / e.p.tn;
@@ -1659,7 +1699,7 @@ int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, 
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-        cudaLaunchKernelEx(&cfg, conv_umma_kernel, pl->tmA, pl->tmB, p);
+        cudaLaunchKernelEx(&cfg, conv_umma_kernel, pl->tmA, pl->tmB, pl->tmP, p);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return hbp_cuda_fail(e, "conv_umma_kernel", __FILE__, __LINE__);

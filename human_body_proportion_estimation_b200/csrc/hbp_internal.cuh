@@ -10,7 +10,18 @@
 
 struct HrnetModel;   // hrnet.cu
 
-enum { HBP_SCRATCH_SLOTS = 24, HBP_TIMER_SLOTS = 8 };
+enum { HBP_SCRATCH_SLOTS = 24, HBP_TIMER_SLOTS = 8, HBP_PIPE_SLOTS = 2 };
+
+// one in-flight frame batch of the asynchronous pipeline (hbp_pose_pipeline_submit / _collect)
+struct hbp_pipe_slot {
+    uint8_t* d_frames = nullptr; size_t frames_cap = 0;
+    uint8_t* d_misc = nullptr;   size_t misc_cap = 0;     // parameter block | result block
+    uint8_t* h_pin = nullptr;    size_t pin_cap = 0;      // pinned mirror of d_misc
+    cudaEvent_t ev_h2d = nullptr, ev_crop = nullptr, ev_done = nullptr;
+    bool crop_recorded = false, busy = false;
+    int P = 0;
+    size_t par_bytes = 0, res_bytes = 0;
+};
 
 struct hbp_ctx {
     int device = 0;
@@ -28,6 +39,9 @@ struct hbp_ctx {
     size_t pinned_bytes = 0;
     void* l2_flush = nullptr;
     HrnetModel* hrnet = nullptr;
+    cudaStream_t copy_stream = nullptr;      // host->device copies of the asynchronous pipeline
+    hbp_pipe_slot pipe[HBP_PIPE_SLOTS];
+    uint64_t pipe_seq = 0;
 };
 
 enum { ATTR_CROP = 1, ATTR_CONV = 2, ATTR_UMMA = 4, ATTR_NMS = 8 };

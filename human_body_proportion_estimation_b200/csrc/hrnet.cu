@@ -244,50 +244,57 @@ void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const
             group_of_level[L] = (int)m.ops.size() - 1;
         }
     }
-    // upsample-adds: output i (< nb-1) needs its 1x1 terms (level 1) and its chains (closed at level i)
+    // upsample-adds: output i (< nb-1) needs its 1x1 terms (level 1) and its chains (closed at level i).  Outputs
+    // are grouped by the level they wait for: one launch per group, beside the deeper chain levels on stream 1,
+    // so that only the smallest output (and the last chain link) is left after the last-but-one level.
     {
+        static const bool split = getenv("HBP_UPADD_SPLIT") ? atoi(getenv("HBP_UPADD_SPLIT")) != 0 : true;
         const int n_up = std::min(n_out, nb - 1);
-        const int need_level = std::max(1, n_up - 1);
-        const bool side = grouped && need_level < n_levels;      // deeper chain levels still to run: beside them, on stream 1
-        std::vector<int> members;
-        int join_flag = 0;
-        for (int i = 0; i < n_up; ++i) {
-            HOp op;
-            op.kind = OP_UPADD;
-            op.name = pre + S(".fuse_layers.%d.upadd", i);
-            op.in = lows[i][0];
-            op.in2 = lows[i].size() > 1 ? lows[i][1] : -1;
-            op.in3 = lows[i].size() > 2 ? lows[i][2] : -1;
-            op.up = ups[i][0];
-            op.up2 = ups[i].size() > 1 ? ups[i][1] : 1;
-            op.up3 = ups[i].size() > 2 ? ups[i][2] : 1;
-            op.res = acc[i]; op.out = y[i];
-            op.cin = op.cout = ch[i];
-            op.relu = 1;
-            op.stream = side ? 1 : 0;
-            op.join_before = B.pending_join ? 1 : 0;
-            if (B.pending_join) B.last_join_op = (int)m.ops.size();
-            B.pending_join = false;
-            join_flag |= op.join_before;
-            if (grouped) { op.join_before = 0; op.grouped = 1; }
-            m.ops.push_back(op);
-            B.wrote(op.out, (int)m.ops.size() - 1);
-            members.push_back((int)m.ops.size() - 1);
-        }
-        if (grouped && !members.empty()) {
-            HOp g;
-            g.kind = OP_UPADD_GROUP;
-            g.name = pre + ".fuse_upadd";
-            g.members = members;
-            g.stream = side ? 1 : 0;
-            g.join_before = join_flag;
-            if (side) {
-                g.wait_ops.push_back(group_of_level[need_level]);
-                m.ops[group_of_level[need_level]].signal = 1;
+        const int max_need = std::max(1, n_up - 1);
+        for (int need_level = 1; need_level <= max_need; ++need_level) {
+            const bool side = grouped && need_level < n_levels;      // deeper chain levels still to run: beside them, on stream 1
+            std::vector<int> members;
+            int join_flag = 0;
+            for (int i = 0; i < n_up; ++i) {
+                const int need_i = split ? std::max(1, i) : max_need;
+                if (need_i != need_level) continue;
+                HOp op;
+                op.kind = OP_UPADD;
+                op.name = pre + S(".fuse_layers.%d.upadd", i);
+                op.in = lows[i][0];
+                op.in2 = lows[i].size() > 1 ? lows[i][1] : -1;
+                op.in3 = lows[i].size() > 2 ? lows[i][2] : -1;
+                op.up = ups[i][0];
+                op.up2 = ups[i].size() > 1 ? ups[i][1] : 1;
+                op.up3 = ups[i].size() > 2 ? ups[i][2] : 1;
+                op.res = acc[i]; op.out = y[i];
+                op.cin = op.cout = ch[i];
+                op.relu = 1;
+                op.stream = side ? 1 : 0;
+                op.join_before = B.pending_join ? 1 : 0;
+                if (B.pending_join) B.last_join_op = (int)m.ops.size();
+                B.pending_join = false;
+                join_flag |= op.join_before;
+                if (grouped) { op.join_before = 0; op.grouped = 1; }
+                m.ops.push_back(op);
+                B.wrote(op.out, (int)m.ops.size() - 1);
+                members.push_back((int)m.ops.size() - 1);
             }
-            m.ops.push_back(g);
-            // program order = issue order: the side-stream launch is recorded after the deeper levels
-            // were pushed, but it only waits for `need_level` through its event
+            if (grouped && !members.empty()) {
+                HOp g;
+                g.kind = OP_UPADD_GROUP;
+                g.name = pre + S(".fuse_upadd%d", need_level);
+                g.members = members;
+                g.stream = side ? 1 : 0;
+                g.join_before = join_flag;
+                if (side) {
+                    g.wait_ops.push_back(group_of_level[need_level]);
+                    m.ops[group_of_level[need_level]].signal = 1;
+                }
+                m.ops.push_back(g);
+                // program order = issue order: the side-stream launch is recorded after the deeper levels
+                // were pushed, but it only waits for `need_level` through its event
+            }
         }
     }
     for (int t : temps) B.release(t, false);

@@ -281,6 +281,49 @@ class Engine:
         return out
 
 
+def _pipeline_async_methods():
+    """submit / collect: the asynchronous form of Engine.pose_pipeline (two batches in flight)."""
+
+    def pose_pipeline_submit(self, frames, mats, frame_idx, boxes_yxyx_px, height_cm,
+                             joint_thr=KEYPOINT_THRES_LIST, swap_rb=True, quarter_offset=False):
+        """Enqueue one batch (same arguments as pose_pipeline) and return a ticket.  Submitting batch
+        n+1 before collecting batch n overlaps its frame upload with the network of batch n.  `frames`
+        should be pinned (Engine.pinned_empty) and must not be modified until the ticket is collected."""
+        frames = _c(frames, np.uint8)
+        if frames.ndim == 3:
+            frames = frames[None]
+        mats = _c(mats, np.float64).reshape(-1, 6)
+        P = mats.shape[0]
+        fi = _c(frame_idx, np.int32)
+        boxes = _c(boxes_yxyx_px, np.float32).reshape(P, 4)
+        hcm = _c(np.broadcast_to(np.asarray(height_cm, np.float64), (P,)), np.float64)
+        thr = _c(joint_thr, np.float32)
+        prm = _capi.PipelineParams(frames.shape[0], frames.shape[1], frames.shape[2], P, int(swap_rb),
+                                   int(quarter_offset), F16)
+        ticket = C.c_int(-1)
+        check(self._lib.hbp_pose_pipeline_submit(self._ctx, C.byref(prm), ptr(frames), ptr(mats), ptr(fi), ptr(boxes),
+                                                 ptr(hcm), ptr(thr), C.byref(ticket)))
+        if not hasattr(self, "_inflight"):
+            self._inflight = {}
+        self._inflight[ticket.value] = (frames, P)          # keeps the frame buffer alive until collect
+        return ticket.value
+
+    def pose_pipeline_collect(self, ticket):
+        """Wait for a submitted batch -> the dict pose_pipeline returns (without heatmaps)."""
+        _, P = self._inflight.pop(ticket)
+        out = dict(kpts_img=np.zeros((P, 17, 2), np.float32), scores=np.zeros((P, 17), np.float32),
+                   ignored=np.zeros((P,), np.uint32), lengths_cm=np.zeros((P, 11), np.float32),
+                   torso_cm=np.zeros((P,), np.float64))
+        check(self._lib.hbp_pose_pipeline_collect(self._ctx, ticket, ptr(out["kpts_img"]), ptr(out["scores"]),
+                                                  ptr(out["ignored"]), ptr(out["lengths_cm"]), ptr(out["torso_cm"])))
+        return out
+
+    return pose_pipeline_submit, pose_pipeline_collect
+
+
+Engine.pose_pipeline_submit, Engine.pose_pipeline_collect = _pipeline_async_methods()
+
+
 def lengths_to_dict(lengths_row, torso):
     """(11,) float32 + float64 torso -> the reference's dict
     (pose_estimator.py:191-200): np.float32 values, np.float64 torso, or the

@@ -243,6 +243,18 @@ HBP_API int hbp_pose_pipeline(hbp_ctx* ctx, const hbp_pipeline_params* prm, cons
                       float* kpts_img, float* scores, uint32_t* ignored,
                       float* lengths_cm, double* torso_cm, void* heatmaps_out);
 
+/* Asynchronous form of hbp_pose_pipeline: up to two batches in flight.  submit() enqueues the
+ * host->device copies on a copy stream and the kernels on the context's stream and returns a ticket;
+ * collect() waits for that batch and copies the results out.  Calling submit(n+1) before collect(n)
+ * overlaps the frame upload of n+1 with the network of n.  `frames` must stay valid (ideally
+ * pinned, hbp_host_alloc) until the batch has been collected.  Same arrays as hbp_pose_pipeline;
+ * heatmaps stay on the device. */
+HBP_API int hbp_pose_pipeline_submit(hbp_ctx* ctx, const hbp_pipeline_params* prm, const uint8_t* frames,
+                             const double* M, const int* frame_idx, const float* boxes,
+                             const double* height_cm, const float* joint_thr, int* ticket);
+HBP_API int hbp_pose_pipeline_collect(hbp_ctx* ctx, int ticket, float* kpts_img, float* scores,
+                              uint32_t* ignored, float* lengths_cm, double* torso_cm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -375,6 +375,39 @@ def test_pipeline_end_to_end(eng, hrnet32):
     assert clear.sum() > 0 and (d[clear] <= 0.5).all()
 
 
+def test_pipeline_async_matches_sync(eng, hrnet32):
+    """hbp_pose_pipeline_submit/_collect (two batches in flight, frame upload overlapped with the network of the
+    previous batch) returns exactly what the synchronous hbp_pose_pipeline returns, batch after batch."""
+    from human_body_proportion_estimation_b200 import geometry
+    frames = [synth.frame_u8(seed=40 + i) for i in range(3)]
+    batches = []
+    for i, fr in enumerate(frames):
+        n = 5 + 3 * i
+        boxes = synth.person_boxes_yxyx_px(n, seed=synth.SEED_BASE + 20 + i, hmin=200, hmax=800)
+        mats = geometry.crop_and_resize_matrices(boxes / np.array([1080, 1920, 1080, 1920], np.float32), 1080, 1920, 256, 192)
+        batches.append((fr, mats, np.zeros(n, np.int32), boxes))
+    # settle the activation-buffer capacity first: conv plans (halo vs per-tap mode, hence the fp32 summation
+    # order inside a conv) are chosen per capacity, so outputs are bit-reproducible per capacity, not across
+    eng.pose_pipeline(*batches[-1], 175)
+    want = [eng.pose_pipeline(fr, mats, fi, boxes, 170 + i) for i, (fr, mats, fi, boxes) in enumerate(batches)]
+    tickets, got = [], []
+    for i, (fr, mats, fi, boxes) in enumerate(batches):
+        tickets.append(eng.pose_pipeline_submit(fr, mats, fi, boxes, 170 + i))
+        if len(tickets) == 2:                              # at most two in flight
+            got.append(eng.pose_pipeline_collect(tickets.pop(0)))
+    while tickets:
+        got.append(eng.pose_pipeline_collect(tickets.pop(0)))
+    for w, g in zip(want, got):
+        for k in ("kpts_img", "scores", "ignored", "lengths_cm", "torso_cm"):
+            assert np.array_equal(w[k], g[k], equal_nan=True), k
+    # a third submit without a collect is refused, not queued silently
+    t0 = eng.pose_pipeline_submit(*batches[0], 175)
+    t1 = eng.pose_pipeline_submit(*batches[1], 175)
+    with pytest.raises(Exception):
+        eng.pose_pipeline_submit(*batches[2], 175)
+    eng.pose_pipeline_collect(t0); eng.pose_pipeline_collect(t1)
+
+
 def test_hrnet_w48_384x288(eng):
     """reference model size (modules/pose_estimator.py:30, models/conv.py:61)."""
     from oracle.hrnet_fp32 import HRNetFP32
