@@ -441,6 +441,7 @@ struct GroupHeader {
     uint32_t tmem_cols;          // allocation: power of two >= 2 * acc_cols
 };
 
+constexpr int kPGroupBias = 4096;     // floats: sum of the members' output channels (checked by the host)
 constexpr int kPGroupThreads = 320;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 / 6-9 two epilogue teams (alternate items)
 
 __global__ void __launch_bounds__(kPGroupThreads, 1)
@@ -448,7 +449,8 @@ conv_umma_pgroup_kernel(const GroupEntry* __restrict__ table, const __grid_const
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ ConvParams s_p[kMaxGroup];
     __shared__ int s_gx[kMaxGroup];
-    __shared__ __align__(16) float s_bias[kMaxGroup][256];        // all output channels of every member
+    __shared__ __align__(16) float s_bias[kPGroupBias];           // all output channels of every member, member e at s_boff[e]
+    __shared__ int s_boff[kMaxGroup];
     __shared__ __align__(8) unsigned long long s_bar[2 * kMaxPStages + 4];
     __shared__ uint32_t s_tmem;
 
@@ -468,9 +470,16 @@ conv_umma_pgroup_kernel(const GroupEntry* __restrict__ table, const __grid_const
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&table[e].p);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&s_p[e]);
         for (int i = threadIdx.x; i < (int)(sizeof(ConvParams) / 4); i += kPGroupThreads) dst[i] = src[i];
-        const int cout = table[e].p.Cout;
-        const float* bsrc = table[e].p.bias;
-        for (int i = threadIdx.x; i < cout; i += kPGroupThreads) s_bias[e][i] = bsrc[i];
+    }
+    {
+        int boff = 0;
+        for (int e = 0; e < n_members; ++e) {
+            const int cout = table[e].p.Cout;
+            const float* bsrc = table[e].p.bias;
+            for (int i = threadIdx.x; i < cout; i += kPGroupThreads) s_bias[boff + i] = bsrc[i];
+            if (threadIdx.x == 0) s_boff[e] = boff;
+            boff += (cout + 3) & ~3;
+        }
     }
     if ((int)threadIdx.x < n_members) s_gx[threadIdx.x] = table[threadIdx.x].gx;
     if (warp == 0) {
@@ -599,7 +608,7 @@ conv_umma_pgroup_kernel(const GroupEntry* __restrict__ table, const __grid_const
             const __half* res = p.res;
             __half* out = p.out;
             const int ab = cnt & 1, use = cnt >> 1;
-            const float* bias_s = s_bias[e] + n_off;
+            const float* bias_s = s_bias + s_boff[e] + n_off;
             const int Hout = p.Ho * up, Wout = p.Wo * up;
             bool valid[2];
             int pn[2], ph_[2], pw[2];
@@ -1577,6 +1586,11 @@ static int group_launch(hbp_ctx* ctx, HrnetModel& m, int slot_index, const int* 
             acc = std::max(acc, (uint32_t)(e.p.m_tiles * e.p.n_tile));
         }
         for (int i = n; i <= kMaxGroup; ++i) g->hdr.item_begin[i] = items;
+        {
+            int couts = 0;
+            for (int i = 0; i < n; ++i) couts += (g->h[i].p.Cout + 3) & ~3;
+            if (couts > kPGroupBias) { hbp_set_error("group has %d output channels (max %d)", couts, kPGroupBias); return HBP_ERR_INVALID; }
+        }
         slot = (slot + 1023u) & ~1023u;
         int stages = (int)((uint32_t)env_int("HBP_PGROUP_SMEM_KB", 192) * 1024u / slot);
         if (stages > kMaxPStages) stages = kMaxPStages;

@@ -43,9 +43,14 @@ struct Builder {
 
     explicit Builder(HrnetModel& mm) : m(mm) {}
 
-    int new_tensor(int c, int h, int w) {
+    // Channel counts the tensor engine cannot take as they are (HRNet-W48's 48 and 96: its rows are 64 or 128 bytes
+    // of K) are stored padded to the next multiple of 64; the extra channels carry zero weights and zero biases, so
+    // they stay exactly zero through every conv / residual / ReLU and never change a logical channel.
+    static int padc(int c) { return (c > 32 && c % 64 != 0) ? (c + 63) / 64 * 64 : c; }
+    int new_tensor(int c_logical, int h, int w) {
         HTensor t;
-        t.c = c; t.h = h; t.w = w;
+        const int c = padc(c_logical);
+        t.c = c; t.c_l = c_logical; t.h = h; t.w = w;
         const size_t sz = (size_t)c * h * w;
         auto take = [&](std::multimap<size_t, int>& pool) {
             auto it = pool.find(sz);
@@ -101,14 +106,21 @@ struct Builder {
         op.kind = OP_CONV;
         op.name = name;
         op.in = in;
+        const int cout_l = cout;
+        cout = padc(cout_l);
         op.cin = ti.c; op.cout = cout; op.k = k; op.stride = stride; op.up = up; op.relu = relu;
+        op.cin_l = ti.c_l; op.cout_l = cout_l;
         op.res = res;
-        if (out < 0) out = new_tensor(cout, ti.h / stride * up, ti.w / stride * up);
+        if (out < 0) out = new_tensor(cout_l, ti.h / stride * up, ti.w / stride * up);
         op.out = out;
         op.w_off = m.n_weights;
         op.b_off = m.n_biases;
+        op.w_off_l = m.n_weights_l;
+        op.b_off_l = m.n_biases_l;
         m.n_weights += (size_t)k * k * cout * ti.c;
         m.n_biases += cout;
+        m.n_weights_l += (size_t)k * k * cout_l * ti.c_l;
+        m.n_biases_l += cout_l;
         op.stream = cur_stream;
         op.join_before = pending_join ? 1 : 0;
         if (pending_join) last_join_op = (int)m.ops.size();
@@ -185,7 +197,7 @@ void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const
     std::vector<int> y(n_out);
     for (int i = 0; i < n_out; ++i) {
         const HTensor ti = m.tensors[x[i]];
-        y[i] = B.new_tensor(ti.c, ti.h, ti.w);
+        y[i] = B.new_tensor(ti.c_l, ti.h, ti.w);
     }
     const int n_levels = std::max(1, n_out - 1);
     std::vector<int> acc(n_out);                         // running sum of output i so far (starts at the identity term)
@@ -307,7 +319,7 @@ void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const
 
 void hrnet_build_program(HrnetModel& m) {
     m.tensors.clear(); m.ops.clear(); m.buf_elems_per_image.clear();
-    m.n_bufs = 0; m.n_weights = 0; m.n_biases = 0;
+    m.n_bufs = 0; m.n_weights = 0; m.n_biases = 0; m.n_weights_l = 0; m.n_biases_l = 0;
     Builder B(m);
     const int C = m.width;
     const int H2 = m.in_h / 2, W2 = m.in_w / 2;
@@ -317,8 +329,11 @@ void hrnet_build_program(HrnetModel& m) {
         op.kind = OP_STEM1; op.name = "conv1";
         op.cin = 3; op.cout = 64; op.k = 3; op.stride = 2; op.relu = 1;
         op.out = B.new_tensor(64, H2, W2);
+        op.cin_l = 3; op.cout_l = 64;
         op.w_off = m.n_weights; op.b_off = m.n_biases;
+        op.w_off_l = m.n_weights_l; op.b_off_l = m.n_biases_l;
         m.n_weights += 9 * 64 * 3; m.n_biases += 64;
+        m.n_weights_l += 9 * 64 * 3; m.n_biases_l += 64;
         m.ops.push_back(op);
     }
     int x = B.conv("conv2", m.ops[0].out, 64, 3, 2, 1);
@@ -373,8 +388,12 @@ void hrnet_build_program(HrnetModel& m) {
         op.kind = OP_HEAD; op.name = "final_layer";
         op.in = xs[0];
         op.cin = C; op.cout = 17; op.k = 1; op.stride = 1;
+        op.cin = m.tensors[xs[0]].c; op.cin_l = C;
+        op.cout_l = 17;
         op.w_off = m.n_weights; op.b_off = m.n_biases;
-        m.n_weights += (size_t)17 * C; m.n_biases += 17;
+        op.w_off_l = m.n_weights_l; op.b_off_l = m.n_biases_l;
+        m.n_weights += (size_t)17 * op.cin; m.n_biases += 17;
+        m.n_weights_l += (size_t)17 * C; m.n_biases_l += 17;
         op.join_before = 1;
         m.ops.push_back(op);
     }
@@ -785,17 +804,31 @@ int hrnet_load(hbp_ctx* ctx, int width, int in_h, int in_w, const void* w16, siz
     HrnetModel* m = new HrnetModel();
     m->width = width; m->in_h = in_h; m->in_w = in_w;
     hrnet_build_program(*m);
-    if (nw != m->n_weights || nb != m->n_biases) {
-        hbp_set_error("HRNet-W%d expects %zu weights and %zu biases, got %zu / %zu", width, m->n_weights,
-                      m->n_biases, nw, nb);
+    if (nw != m->n_weights_l || nb != m->n_biases_l) {
+        hbp_set_error("HRNet-W%d expects %zu weights and %zu biases, got %zu / %zu", width, m->n_weights_l,
+                      m->n_biases_l, nw, nb);
         delete m;
         return HBP_ERR_INVALID;
     }
     ctx->hrnet = m;
-    HBP_CUDA(cudaMalloc(&m->d_weights, nw * sizeof(__half)));
-    HBP_CUDA(cudaMalloc(&m->d_bias, nb * sizeof(float)));
-    HBP_CUDA(cudaMemcpyAsync(m->d_weights, w16, nw * sizeof(__half), cudaMemcpyHostToDevice, ctx->stream));
-    HBP_CUDA(cudaMemcpyAsync(m->d_bias, bias, nb * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    // caller's blobs (logical channels, hbp_hrnet_describe order) -> device blobs (channels padded with zeros)
+    std::vector<__half> wp(m->n_weights, __float2half(0.f));
+    std::vector<float> bp(m->n_biases, 0.f);
+    const __half* wl = static_cast<const __half*>(w16);
+    for (const HOp& op : m->ops) {
+        if (op.kind != OP_CONV && op.kind != OP_STEM1 && op.kind != OP_HEAD) continue;
+        const int taps = op.kind == OP_HEAD ? 1 : op.k * op.k;
+        const int cout_p = op.kind == OP_HEAD ? 17 : op.cout, cout_l = op.cout_l, cin_p = op.cin, cin_l = op.cin_l;
+        for (int t = 0; t < taps; ++t)
+            for (int co = 0; co < cout_l; ++co)
+                memcpy(&wp[op.w_off + ((size_t)t * cout_p + co) * cin_p], &wl[op.w_off_l + ((size_t)t * cout_l + co) * cin_l],
+                       (size_t)cin_l * sizeof(__half));
+        memcpy(&bp[op.b_off], &bias[op.b_off_l], (size_t)cout_l * sizeof(float));
+    }
+    HBP_CUDA(cudaMalloc(&m->d_weights, m->n_weights * sizeof(__half)));
+    HBP_CUDA(cudaMalloc(&m->d_bias, m->n_biases * sizeof(float)));
+    HBP_CUDA(cudaMemcpyAsync(m->d_weights, wp.data(), m->n_weights * sizeof(__half), cudaMemcpyHostToDevice, ctx->stream));
+    HBP_CUDA(cudaMemcpyAsync(m->d_bias, bp.data(), m->n_biases * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     for (int i = 0; i < kStreams - 1; ++i) {
         HBP_CUDA(cudaStreamCreateWithFlags(&m->side[i], cudaStreamNonBlocking));
         HBP_CUDA(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
@@ -1187,12 +1220,12 @@ extern "C" int hbp_hrnet_describe(int width, int in_h, int in_w, char* buf, size
         int ho = 0, wo = 0;
         if (op.kind == OP_STEM1) { ho = m.in_h / 2; wo = m.in_w / 2; }
         else { ho = m.tensors[op.in].h / op.stride; wo = m.tensors[op.in].w / op.stride; }
-        snprintf(line, sizeof(line), "%s %d %d %d %d %zu %zu %d %d %d\n", op.name.c_str(), op.cin, op.cout, op.k,
-                 op.stride, op.w_off, op.b_off, ho, wo, op.up);
+        snprintf(line, sizeof(line), "%s %d %d %d %d %zu %zu %d %d %d\n", op.name.c_str(), op.cin_l, op.cout_l, op.k,
+                 op.stride, op.w_off_l, op.b_off_l, ho, wo, op.up);
         s += line;
     }
-    if (n_weights) *n_weights = m.n_weights;
-    if (n_biases) *n_biases = m.n_biases;
+    if (n_weights) *n_weights = m.n_weights_l;
+    if (n_biases) *n_biases = m.n_biases_l;
     if (needed) *needed = s.size() + 1;
     if (buf && buf_bytes > 0) {
         const size_t k = std::min(buf_bytes - 1, s.size());

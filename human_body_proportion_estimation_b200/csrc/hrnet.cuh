@@ -8,7 +8,8 @@
 
 // One activation tensor, NHWC fp16: (P, h, w, c); batch dimension decided at run time.
 struct HTensor {
-    int c = 0, h = 0, w = 0;
+    int c = 0, h = 0, w = 0;    // c: channels as stored (padded to the tensor engine's 64-channel rows where needed)
+    int c_l = 0;                // logical channels (what the checkpoint has); channels c_l..c-1 are always zero
     int buf = -1;               // index into the per-batch buffer table
 };
 
@@ -26,8 +27,10 @@ struct HOp {
     int in2 = -1, in3 = -1, up2 = 1, up3 = 1;   // OP_UPADD: out = act(res + up(in) + up2(in2) + up3(in3))
     int cin = 0, cout = 0, k = 1, stride = 1, up = 1;
     int relu = 0;
-    size_t w_off = 0;           // offset (in halfs) into the weight blob: layout [tap][cout][cin]
-    size_t b_off = 0;           // offset (in floats) into the bias blob
+    size_t w_off = 0;           // offset (in halfs) into the DEVICE weight blob: layout [tap][cout][cin], padded channel counts
+    size_t b_off = 0;           // offset (in floats) into the device bias blob
+    int cin_l = 0, cout_l = 0;  // logical channel counts and offsets: the layout of the blobs the caller passes (hbp_hrnet_describe)
+    size_t w_off_l = 0, b_off_l = 0;
     int stream = 0;             // branch stream the op runs on
     int join_before = 0;        // all streams must have finished earlier ops before this op starts
     float sm_share = 0.f;       // > 0: fraction of the SMs this op's persistent launch may occupy (branches run side by side)
@@ -47,7 +50,8 @@ struct HrnetModel {
     std::vector<HOp> ops;
     int n_bufs = 0;
     std::vector<size_t> buf_elems_per_image;   // halfs per image for each buffer
-    size_t n_weights = 0, n_biases = 0;
+    size_t n_weights = 0, n_biases = 0;        // device blobs (padded channels)
+    size_t n_weights_l = 0, n_biases_l = 0;    // caller's blobs (logical channels)
     __half* d_weights = nullptr;
     float* d_bias = nullptr;
     int engine = 0;             // 0 SIMT, 1 tcgen05 (falls back per-op where the shape is unsupported)

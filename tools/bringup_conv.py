@@ -38,6 +38,19 @@ CASES = [
     (64, 32, 24, 64, 64, 3, 1, 1, True, True),      # full batch branch 1
     (64, 16, 12, 128, 128, 3, 1, 1, True, True),    # full batch branch 2
     (64, 8, 6, 256, 256, 3, 1, 1, True, True),      # full batch branch 3
+    # HRNet-W48 384x288 shape classes (48/96 channels are stored padded to 64/128); widths 72/36/18/9
+    (2, 96, 72, 64, 64, 3, 1, 1, True, True),       # 21 W48 branch 0
+    (2, 48, 36, 128, 128, 3, 1, 1, True, True),     # 22 W48 branch 1 (ragged width 36)
+    (2, 96, 72, 256, 64, 3, 1, 1, False, True),     # 23 W48 transition1.0
+    (2, 96, 72, 256, 128, 3, 2, 1, False, True),    # 24 W48 transition1.1
+    (2, 96, 72, 64, 128, 3, 2, 1, True, True),      # 25 W48 fuse 0->1
+    (2, 48, 36, 128, 192, 3, 2, 1, True, True),     # 26 W48 fuse 1->2 (output width 18)
+    (2, 24, 18, 192, 384, 3, 2, 1, True, False),    # 27 W48 fuse 2->3 (output width 9)
+    (2, 96, 72, 64, 64, 3, 2, 1, False, True),      # 28 W48 fuse 0->2/3 first link
+    (2, 48, 36, 128, 64, 1, 1, 1, False, False),    # 29 W48 fuse 1x1 1->0
+    (2, 24, 18, 192, 128, 1, 1, 1, False, False),   # 30 W48 fuse 1x1 2->1
+    (2, 12, 9, 384, 192, 1, 1, 1, False, False),    # 31 W48 fuse 1x1 3->2
+    (2, 12, 9, 384, 64, 1, 1, 1, False, False),     # 32 W48 fuse 1x1 3->0
 ]
 
 
