@@ -1243,7 +1243,10 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
                 if (16 * mt < n * rs - (ksz - 1)) continue;             // every group of the tile inside the M-tiles
                 if (n * h * 2 < 16 * mt && !(n == 1 && h == Ho)) { break; }   // < 50 % useful rows: only if nothing else
                 const long tiles = (long)((capP + n - 1) / n) * (Ho / h) * tiles_w;
-                for (int c = op.cout < 256 ? op.cout : 256; c >= 32; c -= 16) {
+                // (N = 64 tiles for layer1's wide 1x1 convs win 10 us per conv in isolation and lose 80 us per forward
+                // in the network, where their tails overlap the next conv's prologue: HBP_HALO_1X1_NMAX, default off)
+                const int c_top = (ksz == 1 && op.cout >= 256) ? env_int("HBP_HALO_1X1_NMAX", 256) : 256;
+                for (int c = op.cout < c_top ? op.cout : c_top; c >= 32; c -= 16) {
                     if (op.cout % c || mt * c > 512) continue;
                     const long items = tiles * (op.cout / c);
                     const long rounds = (items + sms - 1) / sms;
