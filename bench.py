@@ -77,8 +77,17 @@ class ClockSampler:
                  "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            # nvidia-smi needs a few hundred ms to come up: wait for its first line so that the timed region that
+            # follows is sampled from its start; lines that arrived before `mark()` are dropped
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 3.0:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+        self.first = len(self.lines)
+
+    def mark(self):
+        self.first = len(self.lines)                   # samples from here on belong to the timed region
 
     def _read(self):
         for line in self.proc.stdout:
@@ -94,7 +103,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        region = self.lines[self.first:] or self.lines[-1:]      # (a region shorter than one period: the sample just before it)
+        for ln in region:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -324,9 +334,11 @@ def run_ours(args, rank, world, local_rank):
         step_device()
     eng.sync()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank, period_ms=20) if rank == 0 else None
     barrier()
     eng.sync()
+    if sampler:
+        sampler.mark()
     launches0 = eng.kernel_launches()
     step_ms, hrnet_ms = [], []
     t_wall0 = time.perf_counter()
@@ -367,6 +379,8 @@ def run_ours(args, rank, world, local_rank):
     e2e_steps = max(args.steps, 50)
     sampler2 = ClockSampler(local_rank, period_ms=250) if rank == 0 else None
     barrier()
+    if sampler2:
+        sampler2.mark()
     t0 = time.perf_counter()
     prev = None
     for i in range(e2e_steps):

@@ -12,6 +12,13 @@ struct HrnetModel;   // hrnet.cu
 
 enum { HBP_SCRATCH_SLOTS = 24, HBP_TIMER_SLOTS = 8, HBP_PIPE_SLOTS = 2 };
 
+// PIL-bicubic coefficient tables currently in SC_PRE_COEF (csrc/preprocess.cu)
+struct hbp_pil_cache {
+    bool valid = false;
+    int W = 0, nw = 0, H = 0, nh = 0, ks_h = 0, ks_v = 0, row0 = 0, rows = 0;
+    size_t o_kh = 0, o_bv = 0, o_kv = 0;
+};
+
 // one in-flight frame batch of the asynchronous pipeline (hbp_pose_pipeline_submit / _collect)
 struct hbp_pipe_slot {
     uint8_t* d_frames = nullptr; size_t frames_cap = 0;
@@ -39,12 +46,13 @@ struct hbp_ctx {
     size_t pinned_bytes = 0;
     void* l2_flush = nullptr;
     HrnetModel* hrnet = nullptr;
+    hbp_pil_cache pil;
     cudaStream_t copy_stream = nullptr;      // host->device copies of the asynchronous pipeline
     hbp_pipe_slot pipe[HBP_PIPE_SLOTS];
     uint64_t pipe_seq = 0;
 };
 
-enum { ATTR_CROP = 1, ATTR_CONV = 2, ATTR_UMMA = 4, ATTR_NMS = 8 };
+enum { ATTR_CROP = 1, ATTR_CONV = 2, ATTR_UMMA = 4, ATTR_NMS = 8, ATTR_PIL = 16 };
 
 // scratch slot ids
 enum {

@@ -156,70 +156,130 @@ constexpr int kPilBits = 32 - 8 - 2;
 
 __device__ __forceinline__ int pil_clip8(int v) { return min(max(v >> kPilBits, 0), 255); }
 
-// horizontal pass: rows [row0, row0+rows) of every frame -> tmp (n, rows, nw, 3) u8
+// horizontal pass: rows [row0, row0+rows) of every frame -> tmp (n, rows, nw, 3) u8.
+// One CTA = kPilRows consecutive source rows of one frame: the rows are staged in shared memory with 16-byte
+// loads (a tap window is 3*(2*scale*2+1) scattered bytes per output -- 75 at 4K -> 640 -- which as global byte
+// loads made the kernel 7 % of the HBM roofline), the coefficient table is stored tap-major so that a warp
+// reads one coalesced line per tap, and each coefficient is applied to all staged rows.
+constexpr int kPilRows = 2;
+
 __global__ void __launch_bounds__(256)
 pil_hpass_kernel(const uint8_t* __restrict__ in, int n, int H, int W, int row0, int rows, int nw,
-                 const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, uint8_t* __restrict__ tmp) {
-    const size_t total = (size_t)n * rows * nw;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        const int xx = (int)(t % nw);
-        const int r = (int)((t / nw) % rows);
-        const int f = (int)(t / ((size_t)nw * rows));
-        const int xmin = __ldg(bounds + 2 * xx), xn = __ldg(bounds + 2 * xx + 1);
-        const int* k = kk + (size_t)xx * ksize;
-        const uint8_t* src = in + (((size_t)f * H + row0 + r) * W + xmin) * 3;
-        int s0 = 1 << (kPilBits - 1), s1 = s0, s2 = s0;
-        for (int x = 0; x < xn; ++x) {
-            const int c = __ldg(k + x);
-            s0 += (int)__ldg(src + 3 * x) * c;
-            s1 += (int)__ldg(src + 3 * x + 1) * c;
-            s2 += (int)__ldg(src + 3 * x + 2) * c;
+                 const int* __restrict__ bounds, const int* __restrict__ kk_t, int ksize, uint8_t* __restrict__ tmp) {
+    extern __shared__ __align__(16) uint8_t s_rows[];          // kPilRows x pitch, each row keeps its global 16-byte phase
+    const int groups = (rows + kPilRows - 1) / kPilRows;
+    const int f = blockIdx.x / groups, r0 = (blockIdx.x % groups) * kPilRows;
+    const int nr = min(kPilRows, rows - r0);
+    const int row_bytes = W * 3;
+    const int pitch = ((row_bytes + 15 + 15) / 16) * 16;
+    const uint8_t* frames_end = in + (size_t)n * H * W * 3;
+    int ph[kPilRows];
+#pragma unroll
+    for (int r = 0; r < kPilRows; ++r) {
+        ph[r] = 0;
+        if (r >= nr) continue;
+        const uint8_t* g0 = in + ((size_t)f * H + row0 + r0 + r) * row_bytes;
+        ph[r] = (int)(reinterpret_cast<uintptr_t>(g0) & 15);
+        const uint8_t* ga0 = g0 - ph[r];
+        for (int c = threadIdx.x; c < pitch / 16; c += blockDim.x) {
+            const uint8_t* ga = ga0 + 16 * c;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (ga >= in && ga + 16 <= frames_end) v = __ldg(reinterpret_cast<const uint4*>(ga));
+            else {
+                uint8_t* vb = reinterpret_cast<uint8_t*>(&v);
+                for (int k = 0; k < 16; ++k)
+                    if (ga + k >= in && ga + k < frames_end) vb[k] = __ldg(ga + k);
+            }
+            *reinterpret_cast<uint4*>(s_rows + r * pitch + 16 * c) = v;
         }
-        uint8_t* o = tmp + t * 3;
-        o[0] = (uint8_t)pil_clip8(s0); o[1] = (uint8_t)pil_clip8(s1); o[2] = (uint8_t)pil_clip8(s2);
+    }
+    __syncthreads();
+    for (int xx = threadIdx.x; xx < nw; xx += blockDim.x) {
+        const int xmin = __ldg(bounds + 2 * xx), xn = __ldg(bounds + 2 * xx + 1);
+        int acc[kPilRows][3];
+#pragma unroll
+        for (int r = 0; r < kPilRows; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 1 << (kPilBits - 1);
+        const uint8_t* p0 = s_rows + ph[0] + xmin * 3;
+        const uint8_t* p1 = s_rows + pitch + ph[kPilRows - 1] + xmin * 3;
+        for (int x = 0; x < xn; ++x) {
+            const int c = __ldg(kk_t + (size_t)x * nw + xx);
+            acc[0][0] += (int)p0[3 * x] * c; acc[0][1] += (int)p0[3 * x + 1] * c; acc[0][2] += (int)p0[3 * x + 2] * c;
+            acc[1][0] += (int)p1[3 * x] * c; acc[1][1] += (int)p1[3 * x + 1] * c; acc[1][2] += (int)p1[3 * x + 2] * c;
+        }
+#pragma unroll
+        for (int r = 0; r < kPilRows; ++r) {
+            if (r >= nr) continue;
+            uint8_t* o = tmp + (((size_t)f * rows + r0 + r) * nw + xx) * 3;
+            o[0] = (uint8_t)pil_clip8(acc[r][0]); o[1] = (uint8_t)pil_clip8(acc[r][1]); o[2] = (uint8_t)pil_clip8(acc[r][2]);
+        }
     }
 }
 
-// vertical pass + paste on the pad canvas + /255 + layout
+// pad canvas: every output element = pad_value (the content rectangle is overwritten by the vertical pass)
+template <typename T>
+__global__ void __launch_bounds__(256)
+pil_fill_kernel(T* __restrict__ out, size_t total, int pad_value) {
+    const T v = cvt<T>(pad_value);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) out[t] = v;
+}
+
+// vertical pass over the content rectangle + /255 + layout.  The vertical filter does not mix channels, so a
+// row of the uint8 intermediate is a flat array of nw*3 bytes: one thread = 4 consecutive bytes, one 32-bit load
+// per tap (adjacent threads read adjacent words), all loads of a tap window independent.
 template <typename T>
 __global__ void __launch_bounds__(256)
 pil_vpass_kernel(const uint8_t* __restrict__ tmp, int n, int rows, int row0, int nw, int nh,
                  const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, T* __restrict__ out,
-                 int out_h, int out_w, int ox, int oy, int swap_rb, int pad_value, int nchw, int vertical) {
-    const size_t total = (size_t)n * out_h * out_w;
+                 int out_h, int out_w, int ox, int oy, int swap_rb, int nchw, int vertical) {
+    const int row_bytes = nw * 3;
+    const int groups = (row_bytes + 3) >> 2;
+    const size_t total = (size_t)n * nh * groups;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const bool vec = (row_bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(tmp) & 3) == 0;
+    const size_t plane = (size_t)out_h * out_w;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        const int x = (int)(t % out_w);
-        const int y = (int)((t / out_w) % out_h);
-        const int f = (int)(t / ((size_t)out_w * out_h));
-        int v[3] = {pad_value, pad_value, pad_value};
-        if (y >= oy && y < oy + nh && x >= ox && x < ox + nw) {
-            const int yy = y - oy, xx = x - ox;
-            if (vertical) {
-                const int ymin = __ldg(bounds + 2 * yy) - row0, yn = __ldg(bounds + 2 * yy + 1);
-                const int* k = kk + (size_t)yy * ksize;
-                const uint8_t* src = tmp + (((size_t)f * rows + ymin) * nw + xx) * 3;
-                int s0 = 1 << (kPilBits - 1), s1 = s0, s2 = s0;
+        const int q = (int)(t % groups);
+        const int yy = (int)((t / groups) % nh);
+        const int f = (int)(t / ((size_t)groups * nh));
+        const int j0 = q * 4, nb = min(4, row_bytes - j0);
+        int v[4];
+        if (vertical) {
+            const int ymin = __ldg(bounds + 2 * yy) - row0, yn = __ldg(bounds + 2 * yy + 1);
+            const int* k = kk + (size_t)yy * ksize;
+            const uint8_t* src = tmp + ((size_t)f * rows + ymin) * row_bytes + j0;
+            int a0 = 1 << (kPilBits - 1), a1 = a0, a2 = a0, a3 = a0;
+            if (vec) {
                 for (int r = 0; r < yn; ++r) {
                     const int c = __ldg(k + r);
-                    const uint8_t* q = src + (size_t)r * nw * 3;
-                    s0 += (int)__ldg(q) * c; s1 += (int)__ldg(q + 1) * c; s2 += (int)__ldg(q + 2) * c;
+                    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * row_bytes));
+                    a0 += (int)(w & 0xffu) * c; a1 += (int)((w >> 8) & 0xffu) * c;
+                    a2 += (int)((w >> 16) & 0xffu) * c; a3 += (int)(w >> 24) * c;
                 }
-                v[0] = pil_clip8(s0); v[1] = pil_clip8(s1); v[2] = pil_clip8(s2);
             } else {
-                const uint8_t* q = tmp + (((size_t)f * rows + yy - row0) * nw + xx) * 3;
-                v[0] = __ldg(q); v[1] = __ldg(q + 1); v[2] = __ldg(q + 2);
+                for (int r = 0; r < yn; ++r) {
+                    const int c = __ldg(k + r);
+                    const uint8_t* qq = src + (size_t)r * row_bytes;
+                    a0 += (int)__ldg(qq) * c;
+                    if (nb > 1) a1 += (int)__ldg(qq + 1) * c;
+                    if (nb > 2) a2 += (int)__ldg(qq + 2) * c;
+                    if (nb > 3) a3 += (int)__ldg(qq + 3) * c;
+                }
             }
-        }
-        const int c0 = swap_rb ? v[2] : v[0], c2 = swap_rb ? v[0] : v[2];
-        if (nchw) {
-            const size_t plane = (size_t)out_h * out_w;
-            T* o = out + (size_t)f * 3 * plane + (size_t)y * out_w + x;
-            o[0] = cvt<T>(c0); o[plane] = cvt<T>(v[1]); o[2 * plane] = cvt<T>(c2);
+            v[0] = pil_clip8(a0); v[1] = pil_clip8(a1); v[2] = pil_clip8(a2); v[3] = pil_clip8(a3);
         } else {
-            T* o = out + t * 3;
-            o[0] = cvt<T>(c0); o[1] = cvt<T>(v[1]); o[2] = cvt<T>(c2);
+            const uint8_t* qq = tmp + ((size_t)f * rows + yy - row0) * row_bytes + j0;
+            for (int b = 0; b < 4; ++b) v[b] = b < nb ? (int)__ldg(qq + b) : 0;
+        }
+        const int y = oy + yy;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (b >= nb) break;
+            const int j = j0 + b, x = ox + j / 3;
+            int c = j % 3;
+            if (swap_rb) c = 2 - c;
+            if (nchw) out[((size_t)f * 3 + c) * plane + (size_t)y * out_w + x] = cvt<T>(v[b]);
+            else out[(((size_t)f * out_h + y) * out_w + x) * 3 + c] = cvt<T>(v[b]);
         }
     }
 }
@@ -271,6 +331,10 @@ int launch_pil(hbp_ctx* ctx, const uint8_t* in, int n, int H, int W, void* out, 
                int nw, int nh, int swap_rb, int pad_value, int nchw) {
     // Resample.c ImagingResampleInner: horizontal pass over the source rows the vertical pass needs, then vertical
     const bool need_h = nw != W, need_v = nh != H;
+    // the tables depend on (W, nw, H, nh) only: a stream of equally sized frames builds and uploads them once
+    hbp_pil_cache& pc = ctx->pil;
+    if (!(pc.valid && pc.W == W && pc.nw == nw && pc.H == H && pc.nh == nh)) {
+    pc.valid = false;
     std::vector<int> bh, kh, bv, kv;
     const int ks_h = pil_coeffs(W, nw, bh, kh);
     const int ks_v = pil_coeffs(H, nh, bv, kv);
@@ -281,27 +345,50 @@ int launch_pil(hbp_ctx* ctx, const uint8_t* in, int n, int H, int W, void* out, 
     if (!d_tab) return HBP_ERR_NOMEM;
     std::vector<int> tab;
     tab.reserve(n_tab);
+    {   // horizontal coefficients tap-major: kh_t[x * nw + xx]
+        std::vector<int> kt(kh.size());
+        for (int xx = 0; xx < nw; ++xx)
+            for (int x = 0; x < ks_h; ++x) kt[(size_t)x * nw + xx] = kh[(size_t)xx * ks_h + x];
+        kh.swap(kt);
+    }
     tab.insert(tab.end(), bh.begin(), bh.end()); tab.insert(tab.end(), kh.begin(), kh.end());
     tab.insert(tab.end(), bv.begin(), bv.end()); tab.insert(tab.end(), kv.begin(), kv.end());
     HBP_CUDA(cudaMemcpyAsync(d_tab, tab.data(), n_tab * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     HBP_CUDA(cudaStreamSynchronize(ctx->stream));             // `tab` is a local
-    const int* d_bh = d_tab; const int* d_kh = d_bh + bh.size();
-    const int* d_bv = d_kh + kh.size(); const int* d_kv = d_bv + bv.size();
+    pc.W = W; pc.nw = nw; pc.H = H; pc.nh = nh; pc.ks_h = ks_h; pc.ks_v = ks_v; pc.row0 = row0; pc.rows = rows;
+    pc.o_kh = bh.size(); pc.o_bv = pc.o_kh + kh.size(); pc.o_kv = pc.o_bv + bv.size();
+    pc.valid = true;
+    }
+    const int ks_h = pc.ks_h, ks_v = pc.ks_v, row0 = pc.row0, rows = pc.rows;
+    const int* d_tab = (const int*)ctx->scratch[SC_PRE_COEF];
+    const int* d_bh = d_tab; const int* d_kh = d_tab + pc.o_kh;
+    const int* d_bv = d_tab + pc.o_bv; const int* d_kv = d_tab + pc.o_kv;
     const uint8_t* tmp = in;
     int t_rows = H, t_row0 = 0;
     if (need_h) {
         uint8_t* d_tmp = (uint8_t*)hbp_scratch(ctx, SC_PRE_TMP, (size_t)n * rows * nw * 3);
         if (!d_tmp) return HBP_ERR_NOMEM;
-        const size_t total = (size_t)n * rows * nw;
-        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
-        pil_hpass_kernel<<<blocks, 256, 0, ctx->stream>>>(in, n, H, W, row0, rows, nw, d_bh, d_kh, ks_h, d_tmp);
+        const int groups = (rows + kPilRows - 1) / kPilRows;
+        const size_t smem = (size_t)kPilRows * (((size_t)W * 3 + 30) / 16 * 16);
+        if (smem > 200 * 1024) { hbp_set_error("frame rows of %d pixels do not fit the horizontal pass", W); return HBP_ERR_INVALID; }
+        if (!(ctx->attr_flags & ATTR_PIL)) {
+            HBP_CUDA(cudaFuncSetAttribute(pil_hpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ctx->attr_flags |= ATTR_PIL;
+        }
+        pil_hpass_kernel<<<(unsigned)((size_t)n * groups), 256, smem, ctx->stream>>>(in, n, H, W, row0, rows, nw, d_bh, d_kh, ks_h, d_tmp);
         HBP_LAUNCH_CHECK(ctx);
         tmp = d_tmp; t_rows = rows; t_row0 = row0;
     }
-    const size_t total = (size_t)n * out_h * out_w;
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
+    if (nw != out_w || nh != out_h) {
+        const size_t total = (size_t)n * 3 * out_h * out_w;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
+        pil_fill_kernel<T><<<blocks, 256, 0, ctx->stream>>>((T*)out, total, pad_value);
+        HBP_LAUNCH_CHECK(ctx);
+    }
+    const size_t total = (size_t)n * nh * (((size_t)nw * 3 + 3) / 4);
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 32);
     pil_vpass_kernel<T><<<blocks, 256, 0, ctx->stream>>>(tmp, n, t_rows, t_row0, nw, nh, d_bv, d_kv, ks_v, (T*)out, out_h, out_w,
-                                                         ox, oy, swap_rb, pad_value, nchw, need_v ? 1 : 0);
+                                                         ox, oy, swap_rb, nchw, need_v ? 1 : 0);
     HBP_LAUNCH_CHECK(ctx);
     return HBP_OK;
 }
