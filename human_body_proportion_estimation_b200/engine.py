@@ -414,3 +414,41 @@ class MultiGpuEngine:
             for k, v in out.items():
                 merged[k][sel] = v
         return merged
+
+    def stream(self, frame_source, n_frames, depth=2):
+        """Frame stream sharded over the GPUs (BASELINE configs[4]): frame f goes to GPU f mod G, every GPU keeps
+        `depth` (<= 2) frames in flight through pose_pipeline_submit/_collect, one host thread per GPU.
+        `frame_source(f)` -> (frame_u8 (h,w,3) [ideally pinned], mats (P,6), boxes_yxyx_px (P,4), height_cm).
+        Returns (results in frame order, per-frame latency in ms measured submit -> collect)."""
+        import time
+        G = len(self.engines)
+        results, latency = [None] * n_frames, [0.0] * n_frames
+        errors = []
+
+        def work(r):
+            try:
+                eng = self.engines[r]
+                pending = []                        # (frame index, ticket, t_submit)
+                for f in range(r, n_frames, G):
+                    frame, mats, boxes, hcm = frame_source(f)
+                    fi = np.zeros(len(boxes), np.int32)
+                    t0 = time.perf_counter()
+                    pending.append((f, eng.pose_pipeline_submit(frame, mats, fi, boxes, hcm), t0))
+                    if len(pending) >= depth:
+                        g, tk, ts = pending.pop(0)
+                        results[g] = eng.pose_pipeline_collect(tk)
+                        latency[g] = (time.perf_counter() - ts) * 1e3
+                for g, tk, ts in pending:
+                    results[g] = eng.pose_pipeline_collect(tk)
+                    latency[g] = (time.perf_counter() - ts) * 1e3
+            except Exception as exc:      # surfaced after the join
+                errors.append(exc)
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(G)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return results, latency

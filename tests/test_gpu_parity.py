@@ -408,6 +408,27 @@ def test_pipeline_async_matches_sync(eng, hrnet32):
     eng.pose_pipeline_collect(t0); eng.pose_pipeline_collect(t1)
 
 
+def test_multi_gpu_engine_stream_matches_sync():
+    """configs[4] path: MultiGpuEngine.stream (frame f -> GPU f mod G, two frames in flight per GPU) returns per frame
+    what the synchronous single-GPU call returns; runs on however many GPUs the box has (1 at least)."""
+    from human_body_proportion_estimation_b200 import geometry
+    from human_body_proportion_estimation_b200.engine import MultiGpuEngine
+    mg = MultiGpuEngine(width=32, in_h=256, in_w=192, seed=0)
+    frames = [synth.frame_u8(540, 960, seed=70 + i) for i in range(5)]
+    sets = []
+    for i in range(5):
+        boxes = synth.person_boxes_yxyx_px(7, 540, 960, seed=synth.SEED_BASE + 80 + i, hmin=100, hmax=400)
+        mats = geometry.crop_and_resize_matrices(boxes / np.array([540, 960, 540, 960], np.float32), 540, 960, 256, 192)
+        sets.append((mats.reshape(-1, 6), boxes))
+    res, lat = mg.stream(lambda f: (frames[f], sets[f][0], sets[f][1], 170.0 + f), 5)
+    e0 = mg.engines[0]
+    for f in range(5):
+        want = e0.pose_pipeline(frames[f], sets[f][0], np.zeros(7, np.int32), sets[f][1], 170.0 + f)
+        for k in ("kpts_img", "scores", "ignored", "lengths_cm", "torso_cm"):
+            assert np.array_equal(want[k], res[f][k], equal_nan=True), (f, k)
+    assert len(lat) == 5 and min(lat) > 0
+
+
 def test_hrnet_w48_384x288(eng):
     """reference model size (modules/pose_estimator.py:30, models/conv.py:61)."""
     from oracle.hrnet_fp32 import HRNetFP32
