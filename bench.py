@@ -187,6 +187,25 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def hrnet_traffic():
+    """DRAM bytes per HRNet launch from the committed ncu launch list (profiles/*_hrnet_traffic.json, written by
+    tools/launch_summary.py): bench.py cannot run ncu on itself."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    best = None
+    try:
+        for f in sorted(os.listdir(os.path.join(here, "profiles"))):
+            if f.endswith("_hrnet_traffic.json"):
+                best = os.path.join(here, "profiles", f)
+        if best:
+            d = json.load(open(best))
+            d["note"] = "dram__bytes_read+write per launch, average over the %d launches of one forward (%s)" % (
+                round(d["launches_per_forward"]), os.path.basename(best))
+            return d
+    except Exception:
+        pass
+    return {}
+
+
 def config_dict():
     return {"workload": "configs[1]: HRNet-W32 256x192 fp16, 64 synthetic person crops from one 1080p frame "
                         "per step per GPU (crop -> HRNet -> decode+proportions)",
@@ -475,7 +494,8 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "HRNet conv stack: %d launches per step (conv_umma_halo_kernel, conv_umma_pgroup_kernel (one per fuse level), conv_umma_kernel, upsample_add_group, stem, head), one CUDA graph" % n_conv_launch,
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                     "peak_source": pk["src"], "traffic": None,
+                     "peak_source": pk["src"], "traffic": hrnet_traffic().get("dram_bytes_per_launch"),
+                     "traffic_note": hrnet_traffic().get("note"),
                      "flop_per_launch_avg": flops_crop * P / n_conv_launch,
                      "launch_ms_avg": hr_ms / n_conv_launch, "hrnet_ms": hr_ms},
         "cpu_baseline": cpu,

@@ -15,7 +15,8 @@ echo "ncu list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_umma_halo -s 60 -c 4 \
     -o gpurun_out/prof_halo_$TAG -f python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1
 echo "ncu halo rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_umma_pgroup -s 6 -c 3 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_umma_pgroup -s 8 -c 3 \
     -o gpurun_out/prof_pgroup_$TAG -f python bench.py --steps 2 --warmup 3 >> gpurun_out/ncu_full.log 2>&1
 echo "ncu pgroup rc=$?"
+timeout 300 python tools/w48_time.py > gpurun_out/w48_time_$TAG.log 2>&1; cat gpurun_out/w48_time_$TAG.log
 ls gpurun_out | wc -l

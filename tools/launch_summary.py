@@ -33,6 +33,18 @@ def main():
     for k, (n, t, d) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("| %s | %s | %s | %.1f | %.1f | %.0f | %.1f | %.1f |" % (k[0], k[1], k[2], n / fw, t / n / 1e3, t / fw / 1e3, 100 * t / tot, d / fw / 1e6))
     print("total us/fwd: %.0f   DRAM MB/fwd: %.1f" % (tot / fw / 1e3, dram_tot / fw / 1e6))
+    # HRNet conv stack only (what bench.py's `roofline` describes): launches, serialised time and DRAM bytes per forward
+    hr = [(k, v) for k, v in agg.items() if k[0].startswith(("conv_umma", "stem1", "head_kernel", "upsample_add"))]
+    n_l = sum(v[0] for _, v in hr) / fw
+    t_l = sum(v[1] for _, v in hr) / fw
+    d_l = sum(v[2] for _, v in hr) / fw
+    print("HRNet stack: %.0f launches/fwd, %.0f us/fwd serialised, DRAM %.1f MB/fwd (%.2f MB per launch)" % (n_l, t_l / 1e3, d_l / 1e6, d_l / 1e6 / max(n_l, 1)))
+    if len(sys.argv) > 3:
+        import json
+        json.dump({"source": path, "forwards": fw, "launches_per_forward": n_l, "dram_bytes_per_forward": d_l,
+                   "dram_bytes_per_launch": d_l / max(n_l, 1), "serialised_us_per_forward": t_l / 1e3,
+                   "how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over bench.py; HRNet kernels only"},
+                  open(sys.argv[3], "w"), indent=1)
 
 
 if __name__ == "__main__":
