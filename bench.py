@@ -139,6 +139,14 @@ def cpu_reference_run(n_crops, steps, warmup, weights=None):
     if weights is None:
         weights = hrnet_arch.random_weights(WIDTH, IN_H, IN_W, seed=0)
     net = HRNetFP32(weights, WIDTH)
+    # all the host threads the process may use: torchrun exports OMP_NUM_THREADS=1 for every rank, which would time
+    # the reference single-threaded at N > 1
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    if torch.get_num_threads() < avail:
+        torch.set_num_threads(avail)
     cores = torch.get_num_threads()
     if have_cv2:
         cv2.setNumThreads(cores)
@@ -184,7 +192,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": note},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def hrnet_traffic():
@@ -503,11 +511,29 @@ def run_ours(args, rank, world, local_rank):
         "stage_rooflines": stage_rf,
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     grp.close()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line of the contract, on the process's original stdout"""
+    data = (line + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line + "\n"); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries print to file descriptor 1 on their own (NCCL: "NCCL version ..." at communicator creation, more with
+    # NCCL_DEBUG): everything but the JSON line goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
