@@ -516,15 +516,22 @@ int hbp_pose_pipeline_submit(hbp_ctx* ctx, const hbp_pipeline_params* prm, const
                              const double* M, const int* frame_idx, const float* boxes,
                              const double* height_cm, const float* joint_thr, int* ticket) {
     BIND(ctx);
-    HBP_REQUIRE(prm && frames && M && frame_idx && boxes && height_cm && joint_thr && ticket, "null argument");
+    HBP_REQUIRE(prm && ticket, "null argument");
+    HBP_REQUIRE(prm->P == 0 || (frames && M && frame_idx && boxes && height_cm && joint_thr), "null argument");
     if (!ctx->hrnet) { hbp_set_error("hbp_pose_pipeline_submit before hbp_hrnet_load"); return HBP_ERR_STATE; }
     const int P = prm->P;
-    HBP_REQUIRE(P > 0 && prm->n_frames > 0 && prm->h > 0 && prm->w > 0, "bad shape");
+    HBP_REQUIRE(P >= 0 && prm->n_frames > 0 && prm->h > 0 && prm->w > 0, "bad shape");
     for (int p = 0; p < P; ++p)
         HBP_REQUIRE(frame_idx[p] >= 0 && frame_idx[p] < prm->n_frames, "frame_idx out of range");
     const int k = (int)(ctx->pipe_seq % HBP_PIPE_SLOTS);
     hbp_pipe_slot& sl = ctx->pipe[k];
     if (sl.busy) { hbp_set_error("pipeline slot %d has not been collected (at most %d batches in flight)", k, HBP_PIPE_SLOTS); return HBP_ERR_STATE; }
+    if (P == 0) {                            // a frame without persons: nothing to enqueue, collect() returns at once
+        sl.busy = true; sl.P = 0;
+        *ticket = k;
+        ctx->pipe_seq++;
+        return HBP_OK;
+    }
     if (!ctx->copy_stream) HBP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (!sl.ev_h2d) {
         HBP_CUDA(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
@@ -591,6 +598,7 @@ int hbp_pose_pipeline_collect(hbp_ctx* ctx, int ticket, float* kpts_img, float* 
     HBP_REQUIRE(ticket >= 0 && ticket < HBP_PIPE_SLOTS, "bad ticket");
     hbp_pipe_slot& sl = ctx->pipe[ticket];
     if (!sl.busy) { hbp_set_error("ticket %d has nothing in flight", ticket); return HBP_ERR_STATE; }
+    if (sl.P == 0) { sl.busy = false; return HBP_OK; }
     HBP_CUDA(cudaEventSynchronize(sl.ev_done));
     const int P = sl.P, J = 17;
     const size_t r_to = 0, r_k = r_to + (size_t)P * 8, r_s = r_k + (size_t)P * J * 2 * 4,

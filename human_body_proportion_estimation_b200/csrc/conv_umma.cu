@@ -626,11 +626,13 @@ conv_umma_pgroup_kernel(const GroupEntry* __restrict__ table, const __grid_const
                 for (int q = 0; q < 8; ++q)
                     if (cg + q * 8 < n_tile) rq[q] = *reinterpret_cast<const uint4*>(res + o + q * 8);
             };
+            const int dbg = p.dbg_flags;                       // bring-up (HBP_PG_DBG): 1 no stores, 2 no residual, 8 no epilogue work at all
+            if (dbg & 2) res = nullptr;
             if (direct && res && valid[0]) fetch_res(0, 0);
             mbar_wait(acc_full + 8u * ab, (uint32_t)(use & 1));
             tc_fence_after();
             const uint32_t t_base = tmem_base + ((uint32_t)(grp * 32) << 16) + (uint32_t)ab * hdr.acc_cols;
-            for (int mt = 0; mt < m_tiles; ++mt) {
+            for (int mt = 0; mt < ((dbg & 8) ? 0 : m_tiles); ++mt) {
                 for (int cg = 0; cg < n_tile; cg += 64) {
                     if (direct && res && valid[mt] && (mt | cg)) fetch_res(mt, cg);
 #pragma unroll
@@ -673,6 +675,7 @@ conv_umma_pgroup_kernel(const GroupEntry* __restrict__ table, const __grid_const
                                 __align__(16) __half2 pk[8];
 #pragma unroll
                                 for (int q = 0; q < 8; ++q) pk[q] = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+                                if ((dbg & 1) && pk[0].x != __float2half(12345.f)) continue;
                                 *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(&pk[0]);
                                 *reinterpret_cast<uint4*>(out + o + 8) = *reinterpret_cast<const uint4*>(&pk[4]);
                             }
@@ -1579,6 +1582,7 @@ static int group_launch(hbp_ctx* ctx, HrnetModel& m, int slot_index, const int* 
             GroupEntry& e = g->h[i];
             e.tmA = pl->tmA; e.tmB = pl->tmB; e.tmP = pl->tmP; e.p = pl->prm;
             e.p.P = P;
+            e.p.dbg_flags = env_int("HBP_PG_DBG", 0);
             e.p.tl = m.d_timeline ? m.d_timeline + 2 * oi : nullptr;
             const int tiles_n = (P + e.p.tn - 1) / e.p.tn;
             e.gx = tiles_n * e.p.tiles_h * e.p.tiles_w;

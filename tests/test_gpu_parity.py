@@ -406,6 +406,10 @@ def test_pipeline_async_matches_sync(eng, hrnet32):
     with pytest.raises(Exception):
         eng.pose_pipeline_submit(*batches[2], 175)
     eng.pose_pipeline_collect(t0); eng.pose_pipeline_collect(t1)
+    # a frame without persons goes through the same calls and comes back empty
+    fr, mats, fi, boxes = batches[0]
+    empty = eng.pose_pipeline_collect(eng.pose_pipeline_submit(fr, mats[:0], fi[:0], boxes[:0], 175))
+    assert empty["kpts_img"].shape == (0, 17, 2) and empty["lengths_cm"].shape == (0, 11)
 
 
 def test_multi_gpu_engine_stream_matches_sync():
