@@ -244,7 +244,12 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
             const int r0 = min(max(sy, by0), by0 + brows - 1), r1 = min(max(sy + 1, by0), by0 + brows - 1);
             const int base0 = (slots ? 2 * ry : r0 - by0) * pitch + ((src_lo + (r0 * W + bx0) * 3) & 15);
             const int base1 = (slots ? 2 * ry + 1 : r1 - by0) * pitch + ((src_lo + (r1 * W + bx0) * 3) & 15);
-            OutT* orow = obase + (size_t)y * out_w;
+            // channel c goes to plane (swap_rb ? 2 - c : c): the swap is a choice of destination, not of value
+            OutT* orow0 = obase + (size_t)y * out_w + (swap_rb ? 2 * plane : 0);
+            OutT* orow1 = obase + (size_t)y * out_w + plane;
+            OutT* orow2 = obase + (size_t)y * out_w + (swap_rb ? 0 : 2 * plane);
+            // pair stores need every row start 2-element aligned: one uniform test per kernel, not one per store
+            const bool pair_ok = (out_w & 1) == 0 && (plane & 1) == 0 && (reinterpret_cast<uintptr_t>(obase) & (2 * sizeof(OutT) - 1)) == 0;
             for (int x0 = 2 * lane; x0 < out_w; x0 += 64) {
                 const int2 c3 = *reinterpret_cast<const int2*>(&s_cx3[x0]);
                 const uint2 wx = *reinterpret_cast<const uint2*>(&s_wx[x0]);
@@ -266,19 +271,22 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
                     };
                     row(base0 + cc, wr0);
                     row(base1 + cc, wr1);
-                    r[0][k] = finish_acc<OutT>(swap_rb ? acc2 : acc0);
+                    r[0][k] = finish_acc<OutT>(acc0);
                     r[1][k] = finish_acc<OutT>(acc1);
-                    r[2][k] = finish_acc<OutT>(swap_rb ? acc0 : acc2);
+                    r[2][k] = finish_acc<OutT>(acc2);
                 }
+                OutT* const op[3] = {orow0 + x0, orow1 + x0, orow2 + x0};
+                if (pair_ok) {                  // x0 even and out_w even: the pair is inside the row
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    OutT* o = orow + c * plane + x0;
-                    if (x0 + 1 < out_w && (reinterpret_cast<uintptr_t>(o) & (2 * sizeof(OutT) - 1)) == 0) {
-                        if (sizeof(OutT) == 2) *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(r[c]);
-                        else *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(r[c]);
-                    } else {
-                        o[0] = r[c][0];
-                        if (x0 + 1 < out_w) o[1] = r[c][1];
+                    for (int c = 0; c < 3; ++c) {
+                        if (sizeof(OutT) == 2) *reinterpret_cast<uint32_t*>(op[c]) = *reinterpret_cast<const uint32_t*>(r[c]);
+                        else *reinterpret_cast<uint2*>(op[c]) = *reinterpret_cast<const uint2*>(r[c]);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        op[c][0] = r[c][0];
+                        if (x0 + 1 < out_w) op[c][1] = r[c][1];
                     }
                 }
             }
