@@ -1445,7 +1445,7 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     int m_tiles = 2, tn = 0, th = 0, tw = 0;
     {
         bool ok2 = pick_tile(Ho, Wo, 2, &tn, &th, &tw) && 2 * n_tile <= ((op.k == 1 && !persistent_tiling) ? 128 : 256) &&
-                   !(persistent_tiling && op.cin != 32);
+                   !(persistent_tiling && op.cin != 32 && !(op.sm_share > 0.f && !for_group && env_int("HBP_PG_M2", 0)));
         // (persistent walkers want few, large work items: no minimum CTA count, no extra N split)
         if (ok2 && !persistent_tiling) {
             const long ctas = (long)((capP + tn - 1) / tn) * (Ho / th) * (Wo / tw) * (op.cout / n_tile);
