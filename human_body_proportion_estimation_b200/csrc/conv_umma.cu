@@ -271,9 +271,13 @@ __device__ __forceinline__ void conv_umma_body(const CUtensorMap* tmAp, const CU
         const int pad = p.ksz / 2;
         int s = 0;
         uint32_t ph = 0;
-        for (int tap = 0; tap < taps; ++tap) {
-            const int dy = tap / p.ksz - pad, dx = tap % p.ksz - pad;
-            for (int cc = 0; cc < p.n_chunks; ++cc) {
+        // K order = (Cin chunk, dx, dy, 16-channel step), the order of the halo kernel: a conv's fp32 sums, and
+        // with them the network's outputs, do not depend on which of the two kernels a plan picks
+        for (int kk = 0; kk < taps * p.n_chunks; ++kk) {
+            const int cc = kk / taps, tk = kk % taps;
+            const int dxi = tk / p.ksz, dyi = tk % p.ksz, tap = dyi * p.ksz + dxi;
+            const int dy = dyi - pad, dx = dxi - pad;
+            {
                 mbar_wait(empty_bar + 8u * s, ph ^ 1u);
                 if (elect_one()) {
                     mbar_expect_tx(full_bar + 8u * s, p.tx_bytes);
@@ -527,9 +531,11 @@ conv_umma_pgroup_kernel(const GroupEntry* __restrict__ table, const __grid_const
             const uint32_t tx = p.tx_bytes, a_bytes = p.a_stage_bytes;
             const bool phase = p.phase_maps != 0;
             if (p.tl && lane == 0) atomicMin(p.tl, globaltimer_ns());
-            for (int tap = 0; tap < taps; ++tap) {
-                const int dy = tap / ksz - pad, dx = tap % ksz - pad;
-                for (int cc = 0; cc < n_chunks; ++cc) {
+            for (int kk = 0; kk < taps * n_chunks; ++kk) {          // K order (chunk, dx, dy): same as the halo kernel
+                const int cc = kk / taps, tk = kk % taps;
+                const int dxi = tk / ksz, dyi = tk % ksz, tap = dyi * ksz + dxi;
+                const int dy = dyi - pad, dx = dxi - pad;
+                {
                     mbar_wait(empty_bar + 8u * s, ph ^ 1u);
                     if (elect_one()) {
                         mbar_expect_tx(full_bar + 8u * s, tx);

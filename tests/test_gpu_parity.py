@@ -386,9 +386,6 @@ def test_pipeline_async_matches_sync(eng, hrnet32):
         boxes = synth.person_boxes_yxyx_px(n, seed=synth.SEED_BASE + 20 + i, hmin=200, hmax=800)
         mats = geometry.crop_and_resize_matrices(boxes / np.array([1080, 1920, 1080, 1920], np.float32), 1080, 1920, 256, 192)
         batches.append((fr, mats, np.zeros(n, np.int32), boxes))
-    # settle the activation-buffer capacity first: conv plans (halo vs per-tap mode, hence the fp32 summation
-    # order inside a conv) are chosen per capacity, so outputs are bit-reproducible per capacity, not across
-    eng.pose_pipeline(*batches[-1], 175)
     want = [eng.pose_pipeline(fr, mats, fi, boxes, 170 + i) for i, (fr, mats, fi, boxes) in enumerate(batches)]
     tickets, got = [], []
     for i, (fr, mats, fi, boxes) in enumerate(batches):
@@ -431,6 +428,22 @@ def test_multi_gpu_engine_stream_matches_sync():
         for k in ("kpts_img", "scores", "ignored", "lengths_cm", "torso_cm"):
             assert np.array_equal(want[k], res[f][k], equal_nan=True), (f, k)
     assert len(lat) == 5 and min(lat) > 0
+
+
+def test_hrnet_outputs_independent_of_capacity():
+    """Conv plans (halo vs per-tap kernel, tile shapes, N splits) are chosen per activation-buffer capacity; every
+    kernel sums K in the same order (Cin chunk, dx, dy, 16-channel step), so a crop's heatmaps are bit-identical
+    whatever the capacity and whatever else is in the batch."""
+    from human_body_proportion_estimation_b200.engine import Engine
+    e = Engine(0)
+    e.load_hrnet(None, 32, 256, 192, seed=0)
+    crops = np.random.default_rng(3).random((16, 3, 256, 192), dtype=np.float32).astype(np.float16)
+    a5, a8 = e.hrnet_forward(crops[:5]), e.hrnet_forward(crops[:8])           # capacity 8
+    a11 = e.hrnet_forward(crops[:11])                                          # grows the buffers: capacity 16, new plans
+    b5, b8, a16 = e.hrnet_forward(crops[:5]), e.hrnet_forward(crops[:8]), e.hrnet_forward(crops)
+    assert np.array_equal(a8[:5], a5) and np.array_equal(a5, b5) and np.array_equal(a8, b8)
+    assert np.array_equal(a11[:5], b5) and np.array_equal(a16[:11], a11)
+    e.close()
 
 
 def test_hrnet_w48_384x288(eng):
