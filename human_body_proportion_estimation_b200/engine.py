@@ -280,15 +280,12 @@ class Engine:
             out["heatmaps"] = hm
         return out
 
-
-def _pipeline_async_methods():
-    """submit / collect: the asynchronous form of Engine.pose_pipeline (two batches in flight)."""
-
     def pose_pipeline_submit(self, frames, mats, frame_idx, boxes_yxyx_px, height_cm,
                              joint_thr=KEYPOINT_THRES_LIST, swap_rb=True, quarter_offset=False):
-        """Enqueue one batch (same arguments as pose_pipeline) and return a ticket.  Submitting batch
-        n+1 before collecting batch n overlaps its frame upload with the network of batch n.  `frames`
-        should be pinned (Engine.pinned_empty) and must not be modified until the ticket is collected."""
+        """Asynchronous form of pose_pipeline (hbp_pose_pipeline_submit): enqueue one batch and return a
+        ticket; at most two tickets may be outstanding.  Submitting batch n+1 before collecting batch n overlaps
+        its frame upload with the network of batch n.  `frames` should be pinned (Engine.pinned_empty) and must
+        not be modified until the ticket is collected."""
         frames = _c(frames, np.uint8)
         if frames.ndim == 3:
             frames = frames[None]
@@ -317,11 +314,6 @@ def _pipeline_async_methods():
         check(self._lib.hbp_pose_pipeline_collect(self._ctx, ticket, ptr(out["kpts_img"]), ptr(out["scores"]),
                                                   ptr(out["ignored"]), ptr(out["lengths_cm"]), ptr(out["torso_cm"])))
         return out
-
-    return pose_pipeline_submit, pose_pipeline_collect
-
-
-Engine.pose_pipeline_submit, Engine.pose_pipeline_collect = _pipeline_async_methods()
 
 
 def lengths_to_dict(lengths_row, torso):
