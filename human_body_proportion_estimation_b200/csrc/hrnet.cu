@@ -432,11 +432,15 @@ stem1_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const 
         s_w[co * kStemLd + k] = k < 27 ? w[((size_t)(k / 3) * 64 + co) * 3 + (k % 3)] : __float2half(0.f);   // blob layout [tap][co][ci]
     }
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_b[i] = bias[i];
+    __syncthreads();                                   // weights + bias staged once per (persistent) block
     const int Ho = H / 2, Wo = W / 2;
     const size_t total = (size_t)P * Ho * Wo;
-    const size_t pix_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t pix = pix_raw < total ? pix_raw : total - 1;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    // grid-stride over chunks of 128 pixels: the weight staging above (2048 scattered loads + a block barrier) used
+    // to be paid by each of 6144 one-chunk blocks
+    for (size_t chunk = blockIdx.x; chunk * blockDim.x < total; chunk += gridDim.x) {
+    const size_t pix_raw = chunk * blockDim.x + threadIdx.x;
+    const size_t pix = pix_raw < total ? pix_raw : total - 1;
     const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((size_t)Wo * Ho));
     // im2col row of this lane's pixel
     {
@@ -457,7 +461,7 @@ stem1_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const 
 #pragma unroll
         for (int q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4*>(v)[q];
     }
-    __syncthreads();                                   // weights (block) + im2col rows (warp) visible
+    __syncwarp();                                      // im2col rows of this warp visible to its lanes
     const int g = lane >> 2, tq = lane & 3;            // fragment row group / thread-in-quad
     // A fragments: 2 M-tiles (16 pixels) x 2 K-steps
     uint32_t a[2][2][4];
@@ -496,12 +500,14 @@ stem1_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const 
             }
     }
     __syncwarp();
-    const size_t warp_pix0 = (size_t)blockIdx.x * blockDim.x + wrp * 32;
+    const size_t warp_pix0 = chunk * blockDim.x + wrp * 32;
     uint4* o = reinterpret_cast<uint4*>(out + warp_pix0 * 64);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int i = k * 32 + lane, pl = i >> 3, c = i & 7;
         if (warp_pix0 + pl < total) o[i] = s_out[wrp][pl * 8 + (c ^ (pl & 7))];
+    }
+    __syncwarp();                                      // s_a / s_out of this warp are rewritten by its next chunk
     }
 }
 
@@ -949,7 +955,7 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
         if (op.kind == OP_STEM1) {
             const HTensor& to = m->tensors[op.out];
             const size_t total = (size_t)P * to.h * to.w;
-            stem1_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+            stem1_kernel<<<(unsigned)std::min<size_t>((total + 127) / 128, (size_t)ctx->sm_count * 7), 128, 0, st>>>(
                 crops, m->d_weights + op.w_off, m->d_bias + op.b_off, m->bufs[to.buf], P, m->in_h, m->in_w);
         } else if (op.kind == OP_HEAD) {
             const HTensor& ti = m->tensors[op.in];
