@@ -68,6 +68,8 @@ _SIGS = {
     "hbp_hrnet_set_engine": (_I, [_P, _I]),
     "hbp_hrnet_debug_tensor": (_I, [_P, _I, _P, C.c_size_t, C.POINTER(_I), C.POINTER(_I),
                                     C.POINTER(_I), C.POINTER(_I)]),
+    "hbp_hrnet_forward_until": (_I, [_P, _P, _I, _I, _I]),
+    "hbp_hrnet_op_name": (_I, [_P, _I, C.c_char_p, C.c_size_t, C.POINTER(_I)]),
     "hbp_decode_proportions": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P,
                                     _P, _P, _I]),
     "hbp_pose_pipeline": (_I, [_P, C.POINTER(PipelineParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,

@@ -376,6 +376,29 @@ int hbp_hrnet_debug_tensor(hbp_ctx* ctx, int id, void* out_host, size_t max_byte
     return hrnet_debug_tensor(ctx, id, out_host, max_bytes, n, h, w, c);
 }
 
+int hbp_hrnet_forward_until(hbp_ctx* ctx, const void* crops, int P, int op_index, int mem) {
+    BIND(ctx);
+    HBP_REQUIRE(crops && P > 0, "bad arguments");
+    if (!ctx->hrnet) { hbp_set_error("hbp_hrnet_forward_until before hbp_hrnet_load"); return HBP_ERR_STATE; }
+    int ih, iw, wd;
+    hrnet_dims(ctx, &ih, &iw, &wd);
+    Stager st(ctx, mem);
+    const __half* din = st.in((const __half*)crops, (size_t)P * 3 * ih * iw, SC_IN0);
+    if (st.status) return st.status;
+    return hrnet_forward_until(ctx, din, P, op_index);
+}
+
+int hbp_hrnet_op_name(hbp_ctx* ctx, int op_index, char* buf, size_t buf_bytes, int* n_ops) {
+    BIND(ctx);
+    if (!ctx->hrnet) { hbp_set_error("hbp_hrnet_op_name before hbp_hrnet_load"); return HBP_ERR_STATE; }
+    if (n_ops) *n_ops = hrnet_op_count(ctx);
+    if (!buf || buf_bytes == 0) return HBP_OK;
+    const char* nm = hrnet_op_name(ctx, op_index);
+    HBP_REQUIRE(nm != nullptr, "op index out of range");
+    snprintf(buf, buf_bytes, "%s", nm);
+    return HBP_OK;
+}
+
 int hbp_decode_proportions(hbp_ctx* ctx, const void* hm, int dtype, int P, int J, int Hh, int Wh,
                            const float* boxes, const double* height_cm, const float* thr, int quarter,
                            float* kpts_hm, float* kpts_img, float* scores, int32_t* idx,

@@ -77,6 +77,10 @@ struct ConvParams {
     int issuers;                 // halo mode: MMA-issuing warps
     int teams;                   // halo mode: epilogue teams (2 needs an even number of ring stages and accumulator buffers) (2: alternate tiles, one accumulator buffer each)
     int phase_maps;              // stride-2 per-tap mode: the four (row, column) parity planes of the input have their own dense tensor maps
+    int bias_mma;                // halo mode: the bias enters the accumulator through one extra MMA per M-tile (ones x [bias_hi, bias_lo]) instead of the epilogue
+    int res_mma;                 // halo mode: the residual tile (TMA ring) is added by MMAs against a 32x32 identity instead of the epilogue
+    uint32_t c_bytes;            // halo mode: constant operand tiles (ones, identity, bias) between the residual ring and the barriers
+    uint32_t idesc32;            // instruction descriptor with N = 32 (residual MMAs)
     int dbg_flags;               // bring-up experiments: 1 = skip the output stores, 2 = skip the bias loads
     long long* dbg;              // optional phase timestamps (8 per CTA, first 64 CTAs), bring-up only
     unsigned long long* tl;      // optional [start, end] globaltimer stamps of this launch (HBP_TIMELINE)
@@ -751,7 +755,11 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t b_base = a_base + p.a_stages * a_tile_bytes;
     const uint32_t r_base = b_base + p.b_slots * (uint32_t)KS * p.b_stage_bytes;  // residual ring: a_stages x r_chunks x r_chunk_bytes
     const uint32_t r_tile_bytes = p.res_smem ? p.r_chunks * p.r_chunk_bytes : 0u;
-    const uint32_t bar_base = r_base + p.a_stages * r_tile_bytes;
+    // constant operand tiles, 64-byte rows in the SWIZZLE_64B pattern (1024-aligned): ones (128 x K32: K columns 0,1 = 1),
+    // identity (32 x K32), bias (n_tile x K32: K column 0 = fp16(bias), 1 = fp16(bias - column 0))
+    const uint32_t c_base = r_base + p.a_stages * r_tile_bytes;
+    const uint32_t c_ones = c_base, c_ident = c_base + 8192u, c_bias = c_base + 10240u;
+    const uint32_t bar_base = c_base + p.c_bytes;
     const uint32_t a_full = bar_base;                                   // a_stages x n_chunks
     const uint32_t a_empty = a_full + 8u * (kMaxAStages * kMaxChunks);  // a_stages
     const uint32_t b_full = a_empty + 8u * kMaxAStages;                 // b_slots
@@ -779,13 +787,32 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (p.res_smem) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
         }
         for (int i = lane; i < p.a_stages * p.n_chunks; i += 32) mbar_init(a_full + 8u * i, 1);
-        for (int i = lane; i < p.a_stages; i += 32) { mbar_init(a_empty + 8u * i, 1); mbar_init(res_full + 8u * i, 1); mbar_init(res_empty + 8u * i, 4); }
+        for (int i = lane; i < p.a_stages; i += 32) { mbar_init(a_empty + 8u * i, 1); mbar_init(res_full + 8u * i, 1); mbar_init(res_empty + 8u * i, p.res_mma ? 1 : 4); }
         for (int i = lane; i < p.b_slots; i += 32) { mbar_init(b_full + 8u * i, 1); mbar_init(b_empty + 8u * i, 1); }
         for (int i = lane; i < kMaxAccBufs; i += 32) { mbar_init(acc_full + 8u * i, 1); mbar_init(acc_empty + 8u * i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
     for (int i = threadIdx.x; i < p.n_tile; i += kHaloThreads) s_bias[i] = p.bias[n_off + i];
+    if (p.c_bytes) {
+        // element (row r, K column k) of a 64-byte-row SWIZZLE_64B tile: 16-byte chunk (k >> 3) ^ ((r >> 1) & 3) of row r
+        for (uint32_t i = threadIdx.x; i < p.c_bytes / 16u; i += kHaloThreads)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(c_base + 16u * i), "r"(0u) : "memory");
+        __syncthreads();
+        const uint32_t one2 = 0x3C003C00u;                                  // (1.0h, 1.0h)
+        for (uint32_t r = threadIdx.x; r < 128u; r += kHaloThreads)
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(c_ones + r * 64u + (((r >> 1) & 3u) << 4)), "r"(one2) : "memory");
+        for (uint32_t n = threadIdx.x; n < 32u; n += kHaloThreads)
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(c_ident + n * 64u + ((((n >> 3) ^ (n >> 1)) & 3u) << 4) + (n & 7u) * 2u), "h"((unsigned short)0x3C00) : "memory");
+        for (uint32_t n = threadIdx.x; n < (uint32_t)p.n_tile; n += kHaloThreads) {
+            const float b = p.bias[n_off + n];
+            const __half hi = __float2half_rn(b);
+            const __half lo = __float2half_rn(b - __half2float(hi));
+            const uint32_t pk = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(c_bias + n * 64u + (((n >> 1) & 3u) << 4)), "r"(pk) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> tcgen05.mma (async proxy) reads
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -900,6 +927,8 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         constexpr uint32_t kMtStep = 16u * HW * kRow16;
         const uint64_t da0 = make_desc(0, p.row_bytes, HW * p.row_bytes);   // A: 8-row groups one stacked row (HW pixels) apart
         const uint64_t db0 = make_desc(0, p.row_bytes);
+        const uint64_t dc0 = make_desc(0, 64);                                  // constant tiles: 64-byte rows, SWIZZLE_64B
+        const uint64_t dr0 = make_desc(0, p.res_smem ? p.r_row_bytes : 64u);    // residual tile as an A operand
         const uint32_t bstep = p.b_stage_bytes >> 4;                            // one tap of weights in 16-byte units
         const uint32_t idesc = p.idesc, n_tile = (uint32_t)p.n_tile;
         const int T = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
@@ -916,6 +945,14 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
             const uint32_t d_base = tmem_base + ab * acc_stride;
             if (dbg && lane == 0 && j < 16) dbg[32 + 3 * j] = clock64();        // accumulator free
+            if (p.bias_mma) {
+                // D = ones x [bias_hi | bias_lo]^T: overwrites the buffer, needs neither the halo tile nor the weights
+                if (!(p.dbg_flags & 16) && elect_one()) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) umma_f16(d_base + mt * n_tile, dc0 + (c_ones >> 4), dc0 + (c_bias >> 4), idesc, 0u);
+                }
+                __syncwarp();
+            }
             for (int cc = 0; cc < p.n_chunks; ++cc) {
                 mbar_wait(a_full + 8u * (sa * p.n_chunks + cc), pa);
                 if (dbg && cc == 0 && j == 0 && lane == 0) dbg[2] = clock64();
@@ -927,8 +964,8 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     // (every instruction between two MMAs idles the pipe: it queues only ~2 of them)
                     tc_fence_after();
                     const uint64_t b_c = db0 + ((b_base + (uint32_t)(cc * KS) * b_slot_bytes) >> 4);
-                    const uint32_t fresh = cc == 0 ? 0u : 1u;
-                    if (elect_one()) {
+                    const uint32_t fresh = (cc == 0 && !p.bias_mma) ? 0u : 1u;
+                    if (!(p.dbg_flags & 16) && elect_one()) {
 #pragma unroll
                         for (int dx = 0; dx < KS; ++dx)
 #pragma unroll
@@ -951,7 +988,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     if (dbg && cc == 0 && dx == 0 && j == 0 && lane == 0) dbg[3] = clock64();
                     tc_fence_after();
                     const uint64_t b_s = db0 + ((b_base + slot * b_slot_bytes) >> 4);
-                    const uint32_t fresh = (cc == 0 && dx == 0) ? 0u : 1u;      // first MMA of a tile overwrites
+                    const uint32_t fresh = (cc == 0 && dx == 0 && !p.bias_mma) ? 0u : 1u;      // first MMA of a tile overwrites
                     if (elect_one()) {
 #pragma unroll
                         for (int dy = 0; dy < KS; ++dy) {
@@ -968,6 +1005,27 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     __syncwarp();
                     if (!p.b_resident && ++s == p.b_slots) { s = 0; ph ^= 1u; }
                 }
+            }
+            if (p.res_mma) {
+                // D[:, 32j .. 32j+32) += residual[:, 32j .. 32j+32) x I32: the residual tile of the TMA ring (pixel rows in
+                // the hardware swizzle, the A-operand layout) against the identity; exact (fp16 x 1.0 into fp32)
+                mbar_wait(res_full + 8u * sa, pa);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t rst = r_base + sa * r_tile_bytes;
+                    const uint32_t r_ch = p.r_row_bytes >> 1;                     // channels per residual box (32 or 64)
+                    for (int mt = 0; mt < ((p.dbg_flags & 16) ? 0 : MT); ++mt)
+                        for (uint32_t jb = 0; jb < n_tile / 32u; ++jb) {
+                            const uint32_t ch = jb * 32u;
+                            const uint32_t box = rst + (ch / r_ch) * p.r_chunk_bytes + (uint32_t)mt * 128u * p.r_row_bytes;
+                            const uint64_t ad = dr0 + ((box + (ch % r_ch) * 2u) >> 4);
+                            const uint32_t dt = d_base + mt * n_tile + ch;
+                            umma_f16(dt, ad, dc0 + (c_ident >> 4), p.idesc32, 1u);
+                            umma_f16(dt, ad + 2, dc0 + (c_ident >> 4) + 2, p.idesc32, 1u);
+                        }
+                    umma_commit(res_empty + 8u * sa);    // residual stage free when these MMAs retire
+                }
+                __syncwarp();
             }
             if (elect_one()) {
                 umma_commit(a_empty + 8u * sa);          // halo stage free when these MMAs retire
@@ -990,8 +1048,9 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int team = (warp - 4) >> 2;
         const int grp = warp & 3;                               // TMEM lane group this warp may read
         const int r = grp * 32 + lane;
-        const bool has_res = p.res != nullptr;
-        const bool res_smem = p.res_smem != 0;
+        const bool has_res = p.res != nullptr && !p.res_mma;      // (res_mma: the MMA warps already added it)
+        const bool res_smem = p.res_smem != 0 && !p.res_mma;
+        const bool add_bias = !p.bias_mma;
         const uint32_t t_lane0 = tmem_base + ((uint32_t)(grp * 32) << 16);
         const int teams = p.teams;
         const int T = team < teams ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -1013,10 +1072,13 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             rs_xor[mt] = p.r_row_bytes == 128 ? (rrow & 7u) : ((rrow >> 1) & 3u);    // SWIZZLE_128B / SWIZZLE_64B on 1024-aligned boxes
         }
         // 16 residual halfs (two 16-byte chunks) of columns c0..c0+15 of this thread's row, from the ring stage at `rst`
+        // (every per-M-tile quantity is selected with ?: -- indexing the two-element arrays with a run-time `mt` put them
+        // in local memory, and the epilogue then waited on two dependent LDL round trips per 32 columns: r01c ncu source page)
         auto res_lds = [&](uint32_t rst, int mt, int c0, uint4& q0, uint4& q1) {
-            const uint32_t box = rst + (uint32_t)(c0 >> 6) * p.r_chunk_bytes + rs_off[mt];
+            const uint32_t rso = mt ? rs_off[1] : rs_off[0], rsx = mt ? rs_xor[1] : rs_xor[0];
+            const uint32_t box = rst + (uint32_t)(c0 >> 6) * p.r_chunk_bytes + rso;
             const uint32_t ci = (uint32_t)(c0 & 63) >> 3;
-            const uint32_t a0 = box + (((ci) ^ rs_xor[mt]) << 4), a1 = box + (((ci + 1) ^ rs_xor[mt]) << 4);
+            const uint32_t a0 = box + (((ci) ^ rsx) << 4), a1 = box + (((ci + 1) ^ rsx) << 4);
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "r"(a0));
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "r"(a1));
         };
@@ -1049,7 +1111,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             float x[16];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
-                const float4 b4 = (p.dbg_flags & 2) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q4);
+                const float4 b4 = (!add_bias || (p.dbg_flags & 2)) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q4);
                 x[4 * q4] = __uint_as_float(rr[4 * q4]) + b4.x; x[4 * q4 + 1] = __uint_as_float(rr[4 * q4 + 1]) + b4.y;
                 x[4 * q4 + 2] = __uint_as_float(rr[4 * q4 + 2]) + b4.z; x[4 * q4 + 3] = __uint_as_float(rr[4 * q4 + 3]) + b4.w;
             }
@@ -1086,12 +1148,18 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const uint32_t t_lane = t_lane0 + abuf * acc_stride;
             const bool more = j + teams < T;
             const uint32_t rst = r_base + sr * r_tile_bytes;
+            if (dbg && grp == 2 && lane == 0 && j < 16) dbg[160 + 4 * j] = clock64();           // team starts waiting for tile j
             if (res_smem) mbar_wait(res_full + 8u * sr, (uint32_t)(lap_r & 1));
             mbar_wait(acc_full + 8u * abuf, (uint32_t)(k & 1));
             if (dbg && warp == 4 && lane == 0 && j == 0) dbg[5] = clock64();
             if (dbg && grp == 2 && lane == 0 && j < 16) dbg[96 + 2 * j] = clock64();             // accumulator ready
             tc_fence_after();
-            for (int g = 0; g < groups; ++g) {
+            if (p.dbg_flags & 8) {            // bring-up: barrier handshakes only (measures the TMA + MMA side alone)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty + 8u * abuf) : "memory");
+            }
+            for (int g = 0; g < ((p.dbg_flags & 8) ? 0 : groups); ++g) {
                 // 32 accumulator columns -> registers; after the last group the TMEM buffer goes back to the MMA warps
                 const int col = g << 5;
                 const int mt = MT == 1 ? 0 : (col >= p.n_tile ? 1 : 0);
@@ -1101,25 +1169,29 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 tmem_ld16(t_lane + (uint32_t)col, ra);
                 if (two) tmem_ld16(t_lane + (uint32_t)(col + 16), rb);
                 tmem_ld_wait();
+                if (dbg && grp == 2 && lane == 0 && j < 16 && g == 0) dbg[161 + 4 * j] = clock64();   // first 32 columns in registers
                 if (g == groups - 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty + 8u * abuf) : "memory");      // one arrival per epilogue warp
                 }
                 uint4 q[4] = {};
+                const bool ok = mt ? valid[1] : valid[0];
+                const size_t ob = mt ? obase[1] : obase[0];
                 if (res_smem) {
                     res_lds(rst, mt, c0, q[0], q[1]);
                     if (two) res_lds(rst, mt, c0 + 16, q[2], q[3]);
-                } else if (has_res && valid[mt]) {          // residual straight from global memory (shapes the ring does not cover)
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.res + obase[mt] + c0);
+                } else if (has_res && ok) {                 // residual straight from global memory (shapes the ring does not cover)
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.res + ob + c0);
                     q[0] = rp[0]; q[1] = rp[1];
                     if (two) { q[2] = rp[2]; q[3] = rp[3]; }
                 }
-                if (valid[mt]) {
-                    finish16(ra, obase[mt] + c0, c0, q[0], q[1]);
-                    if (two) finish16(rb, obase[mt] + c0 + 16, c0 + 16, q[2], q[3]);
+                if (ok) {
+                    finish16(ra, ob + c0, c0, q[0], q[1]);
+                    if (two) finish16(rb, ob + c0 + 16, c0 + 16, q[2], q[3]);
                 }
             }
+            if (dbg && grp == 2 && lane == 0 && j < 16) dbg[162 + 4 * j] = clock64();           // all stores issued
             if (res_smem) {
                 // residual stage back to the producer
                 __syncwarp();
@@ -1307,7 +1379,15 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     const uint32_t r_box_bytes = (uint32_t)(8 * th * tn) * r_row_bytes;
     const uint32_t r_chunk_bytes = (r_box_bytes + 1023u) & ~1023u;
     const uint32_t a_tile = a_chunk_bytes * n_chunks + (res_smem ? r_chunks * r_chunk_bytes : 0u);     // one ring stage: halo tile + residual tile
-    const uint32_t fixed = kHaloBarBytes + (uint32_t)n_tile * 4 + 1024 + 64;
+    // bias and residual through the tensor pipe (one extra MMA per M-tile / two per 32 output channels), so that the
+    // epilogue issues no shared-memory loads.  Measured (profiles/r02_epilogue_ablation.md): 4.5 % on the 32-channel
+    // branch conv, against 19 % from keeping the per-M-tile row geometry out of local memory; the tensor pipe does not
+    // round like the epilogue's fp32 adds, so a conv would no longer give bit-identical results in the halo and the
+    // per-tap kernels (plans change with the buffer capacity).  Off by default: HBP_HALO_BIAS_MMA=1 / HBP_HALO_RES_MMA=1.
+    const bool bias_mma = env_int("HBP_HALO_BIAS_MMA", 0) != 0;
+    const bool res_mma = res_smem && tn == 1 && n_tile % 32 == 0 && bias_mma && env_int("HBP_HALO_RES_MMA", 1) != 0;
+    const uint32_t c_bytes = bias_mma ? 8192u + 2048u + (((uint32_t)n_tile * 64u + 1023u) & ~1023u) : 0u;
+    const uint32_t fixed = kHaloBarBytes + (uint32_t)n_tile * 4 + 1024 + 64 + c_bytes;
     const int k_slots = ksz * n_chunks;                                 // weight slots per tile: (chunk, dx), ksz taps each
     const uint32_t b_slot = (uint32_t)ksz * b_stage;
     const uint32_t b_all = (uint32_t)k_slots * b_slot;
@@ -1357,6 +1437,8 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     while (cols < (uint32_t)(acc_bufs * m_tiles * n_tile)) cols *= 2;
     p.tmem_cols = cols;
     p.idesc = (1u << 4) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    p.idesc32 = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    p.bias_mma = bias_mma ? 1 : 0; p.res_mma = res_mma ? 1 : 0; p.c_bytes = c_bytes;
     p.mode = 1; p.rs = rs; p.a_chunk_bytes = a_chunk_bytes; p.a_box_bytes = a_box_bytes;
     p.bias = m.d_bias + op.b_off;
     p.res = op.res >= 0 ? m.bufs[m.tensors[op.res].buf] : nullptr;
@@ -1366,8 +1448,8 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     pl->occ = 1;
     pl->sm_budget = sm_budget;
     if (getenv("HBP_CONV_TRACE"))
-        fprintf(stderr, "[plan] %s halo tile tn=%d th=%d m=%d n_tile=%d acc_bufs=%d a_stages=%d b_slots=%d resident=%d tmem=%u smem=%zu tiles=%ld per_cta=%ld sms=%d\n",
-                op.name.c_str(), tn, th, m_tiles, n_tile, acc_bufs, a_stages, b_slots, resident, cols, pl->smem_bytes, tiles, per_cta, sm_budget);
+        fprintf(stderr, "[plan] %s halo tile tn=%d th=%d m=%d n_tile=%d acc_bufs=%d a_stages=%d b_slots=%d resident=%d tmem=%u smem=%zu tiles=%ld per_cta=%ld sms=%d bias_mma=%d res_mma=%d\n",
+                op.name.c_str(), tn, th, m_tiles, n_tile, acc_bufs, a_stages, b_slots, resident, cols, pl->smem_bytes, tiles, per_cta, sm_budget, p.bias_mma, p.res_mma);
 
     EncodeTiledFn enc = get_encode();
     const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -1705,8 +1787,8 @@ int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, 
             for (int j = 0; j < 16; ++j) {
                 auto rel = [&](int k) { return h[k] ? (long long)(h[k] - h[0]) : -1LL; };
                 if (!h[34 + 3 * j]) break;
-                fprintf(stderr, "[timeline] %2d: %6lld | %6lld %6lld %6lld | %6lld %6lld\n", j, rel(128 + j), rel(32 + 3 * j), rel(33 + 3 * j),
-                        rel(34 + 3 * j), rel(96 + 2 * j), rel(97 + 2 * j));
+                fprintf(stderr, "[timeline] %2d: %6lld | %6lld %6lld %6lld | %6lld %6lld | team: wait from %6lld, first ld %6lld, stores issued %6lld\n", j, rel(128 + j), rel(32 + 3 * j), rel(33 + 3 * j),
+                        rel(34 + 3 * j), rel(96 + 2 * j), rel(97 + 2 * j), rel(160 + 4 * j), rel(161 + 4 * j), rel(162 + 4 * j));
             }
             p.dbg = nullptr;
             return HBP_OK;

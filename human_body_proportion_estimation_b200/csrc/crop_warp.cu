@@ -83,8 +83,9 @@ template <typename OutT>
 __global__ void __launch_bounds__(kThreads)
 crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
                  const double* __restrict__ Ms, const int* __restrict__ frame_idx, int P,
-                 int out_h, int out_w, int swap_rb, OutT* __restrict__ out) {
+                 int out_h, int out_w, int swap_rb, OutT* __restrict__ out, const int* __restrict__ live) {
     extern __shared__ __align__(16) uint8_t smem_all[];
+    if (live && (int)blockIdx.y >= *live) return;       // chained pipeline: person slots beyond the device-side count
     uint8_t* const smem = smem_all + kSmemPad;
     __shared__ int s_ad[kMaxTabW], s_bd[kMaxTabW];      // OpenCV's adelta / bdelta tables (per output column)
     // axis-aligned maps (every crop_and_resize box): per column the staged byte offset of the left tap and the
@@ -392,7 +393,7 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
 
 int k_crop_warp(hbp_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w, const double* M,
                 const int* frame_idx, int P, int out_h, int out_w, int swap_rb, void* out,
-                int out_dtype) {
+                int out_dtype, const int* live) {
     if (P <= 0) return HBP_OK;
     if (!(ctx->attr_flags & ATTR_CROP)) {
         HBP_CUDA(cudaFuncSetAttribute(crop_warp_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2 * kSmemPad));
@@ -402,10 +403,10 @@ int k_crop_warp(hbp_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w,
     dim3 grid((out_h + kBandRows - 1) / kBandRows, P);
     if (out_dtype == HBP_F16)
         crop_warp_kernel<__half><<<grid, kThreads, kSmemBudget + 2 * kSmemPad, ctx->stream>>>(
-            frames, n_frames, h, w, M, frame_idx, P, out_h, out_w, swap_rb, (__half*)out);
+            frames, n_frames, h, w, M, frame_idx, P, out_h, out_w, swap_rb, (__half*)out, live);
     else
         crop_warp_kernel<float><<<grid, kThreads, kSmemBudget + 2 * kSmemPad, ctx->stream>>>(
-            frames, n_frames, h, w, M, frame_idx, P, out_h, out_w, swap_rb, (float*)out);
+            frames, n_frames, h, w, M, frame_idx, P, out_h, out_w, swap_rb, (float*)out, live);
     HBP_LAUNCH_CHECK(ctx);
     return HBP_OK;
 }

@@ -237,7 +237,7 @@ nms_mask_kernel(const SortedBox* __restrict__ sorted, const int* __restrict__ n_
     if (j < n) bj = s[j];
     uint32_t* __restrict__ m = mask + (size_t)b * mask_img_stride;
     for (int i = blockIdx.y * 8 + warp; i < n; i += gridDim.y * 8) {
-        if (w * 32 + 31 <= i) continue;             // whole word at or before the diagonal
+        if (w * 32 + 31 < i) continue;              // whole word before the diagonal (the diagonal word itself is written, all zero for row 32w+31: the sweep reads it)
         const SortedBox bi = s[i];
         const bool bit = (j < n) && (j > i) && suppresses(bi, bj, thr, legacy);
         const uint32_t word = __ballot_sync(0xffffffffu, bit);
@@ -406,7 +406,164 @@ int run_nms(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, d
     return HBP_OK;
 }
 
+// The same five kernels with a fixed candidate capacity and NO host read-back (the chained det -> pose
+// pipeline): grids are sized for `cand_cap`, every kernel reads the actual count on the device and exits early.
+// status[b] bit 0 is set when image b had more candidates than cand_cap (the surplus was dropped in arrival order).
+__global__ void nms_overflow_kernel(const int* __restrict__ cand_count, int cap, int B, int* __restrict__ status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && cand_count[b] > cap) atomicOr(status, 1);
+}
+
+int run_nms_bounded(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, double thr,
+                    const int* classes, int n_classes, int max_keep, int cand_cap, float* out_det, int* out_count,
+                    int* status) {
+    if (cand_cap > kMaxWords * 32 || cand_cap % 32) { hbp_set_error("candidate capacity must be a multiple of 32, at most %d", kMaxWords * 32); return HBP_ERR_INVALID; }
+    const int cap = cand_cap;
+    Cand* cand = (Cand*)hbp_scratch(ctx, SC_NMS_CAND, (size_t)B * cap * sizeof(Cand));
+    SortedBox* sorted = (SortedBox*)hbp_scratch(ctx, SC_NMS_SORTED, (size_t)B * cap * sizeof(SortedBox));
+    int* misc = (int*)hbp_scratch(ctx, SC_NMS_MISC, ((size_t)3 * B + (size_t)B * max_keep) * sizeof(int));
+    const int words = cap / 32;
+    const size_t mask_img_stride = (size_t)cap * words;
+    uint32_t* mask = (uint32_t*)hbp_scratch(ctx, SC_NMS_MASK, (size_t)B * mask_img_stride * sizeof(uint32_t));
+    if (!cand || !sorted || !misc || !mask) return HBP_ERR_NOMEM;
+    int* cand_count = misc, *n_sorted = misc + B, *keep_count = misc + 2 * B, *keep = misc + 3 * B;
+    HBP_CUDA(cudaMemsetAsync(misc, 0, (size_t)3 * B * sizeof(int), ctx->stream));
+    {
+        const int warps = (N + 31) / 32;
+        dim3 grid((warps + 7) / 8, B);
+        yolo_filter_kernel<<<grid, 256, 0, ctx->stream>>>(pred, N, nc, conf, 0, classes, n_classes, cand, cand_count, cap);
+        HBP_LAUNCH_CHECK(ctx);
+    }
+    if (status) { nms_overflow_kernel<<<(B + 63) / 64, 64, 0, ctx->stream>>>(cand_count, cap, B, status); HBP_LAUNCH_CHECK(ctx); }
+    dim3 g1((cap + 255) / 256, B);
+    rank_scatter_kernel<<<g1, 256, 0, ctx->stream>>>(cand, cand_count, cap, 0, 30000, 4096.f, sorted, n_sorted);
+    HBP_LAUNCH_CHECK(ctx);
+    dim3 g2(words, 16, B);
+    nms_mask_kernel<<<g2, 256, 0, ctx->stream>>>(sorted, n_sorted, cap, words, mask_img_stride, thr, 0, mask);
+    HBP_LAUNCH_CHECK(ctx);
+    nms_sweep_kernel<<<B, kSweepThreads, 0, ctx->stream>>>(mask, n_sorted, words, mask_img_stride, max_keep, keep, keep_count);
+    HBP_LAUNCH_CHECK(ctx);
+    nms_gather_kernel<<<B, 128, 0, ctx->stream>>>(sorted, cand, cap, keep, keep_count, cand_count, max_keep, 0, out_det, out_count);
+    HBP_LAUNCH_CHECK(ctx);
+    return HBP_OK;
+}
+
+// ---- detections -> per-person crop parameters, on the device --------------------------------------------------
+// One CTA.  Persons are numbered frame by frame in detector order; person p >= persons_cap is dropped (status bit 1).
+// Outputs per person: 2x3 dst->src matrix (double, what hbp_crop_warp takes), the pixel box yxyx (float, what
+// hbp_decode_proportions takes), its frame and its height_cm = heights[min(i, n_heights-1)], i = index inside the
+// frame (person_det_pose_edet4_trtserver.py:166-168).
+//
+// YOLO (configs[2]): det rows [x1,y1,x2,y2,conf,cls] in letterbox pixels -> scale_coords + clip_coords
+// (onnx_utils.py:238-266, the arithmetic of scale_coords_kernel) -> int() truncation, the crop the reference's
+// PoseEstimator.preprocess would take from frame[y1:y2, x1:x2] with cv2.resize (pose_estimator.py:29-45): the
+// half-pixel stretch matrix of geometry.box_resize_matrices.
+__global__ void __launch_bounds__(256)
+persons_from_yolo_kernel(const float* __restrict__ det, const int* __restrict__ det_count, int F, int max_det,
+                         float pad_x, float pad_y, float gain, float w0, float h0, int out_h, int out_w,
+                         const double* __restrict__ heights, int n_heights, int persons_cap,
+                         double* __restrict__ M, float* __restrict__ boxes, int* __restrict__ frame_idx,
+                         double* __restrict__ height_cm, int* __restrict__ n_persons, int* __restrict__ status) {
+    __shared__ int s_off[1025];
+    if (threadIdx.x == 0) {
+        int o = 0;
+        for (int f = 0; f < F; ++f) { s_off[f] = o; o += min(det_count[f], max_det); }
+        s_off[F] = o;
+        *n_persons = min(o, persons_cap);
+        if (o > persons_cap) atomicOr(status, 2);
+    }
+    __syncthreads();
+    for (int f = 0; f < F; ++f) {
+        const int n = s_off[f + 1] - s_off[f];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int p = s_off[f] + i;
+            if (p >= persons_cap) continue;
+            const float* b = det + ((size_t)f * max_det + i) * 6;
+            float x1 = __fdiv_rn(__fsub_rn(b[0], pad_x), gain), y1 = __fdiv_rn(__fsub_rn(b[1], pad_y), gain);
+            float x2 = __fdiv_rn(__fsub_rn(b[2], pad_x), gain), y2 = __fdiv_rn(__fsub_rn(b[3], pad_y), gain);
+            x1 = fminf(fmaxf(x1, 0.f), w0); y1 = fminf(fmaxf(y1, 0.f), h0);
+            x2 = fminf(fmaxf(x2, 0.f), w0); y2 = fminf(fmaxf(y2, 0.f), h0);
+            const int xi1 = (int)x1, yi1 = (int)y1, xi2 = (int)x2, yi2 = (int)y2;
+            const double sx = (double)(xi2 - xi1) / (double)out_w, sy = (double)(yi2 - yi1) / (double)out_h;
+            double* m = M + (size_t)p * 6;
+            m[0] = sx; m[1] = 0.0; m[2] = (double)xi1 + 0.5 * sx - 0.5;
+            m[3] = 0.0; m[4] = sy; m[5] = (double)yi1 + 0.5 * sy - 0.5;
+            float* o = boxes + (size_t)p * 4;
+            o[0] = (float)yi1; o[1] = (float)xi1; o[2] = (float)yi2; o[3] = (float)xi2;
+            frame_idx[p] = f;
+            height_cm[p] = heights[min(i, n_heights - 1)];
+        }
+    }
+}
+
+// EfficientDet (configs[3]): filtered boxes (F, max_persons, 4) yxyx NORMALISED + counts -> tf.image.crop_and_resize
+// matrices (models/conv.py:61-70; geometry.crop_and_resize_matrices in double) and boxes * [h,w,h,w] in float32
+// (person_det_pose_edet4_trtserver.py:145).
+__global__ void __launch_bounds__(256)
+persons_from_edet_kernel(const float* __restrict__ boxes_n, const int* __restrict__ counts, int F, int max_persons,
+                         int img_h, int img_w, int out_h, int out_w, const double* __restrict__ heights, int n_heights,
+                         int persons_cap, double* __restrict__ M, float* __restrict__ boxes, int* __restrict__ frame_idx,
+                         double* __restrict__ height_cm, int* __restrict__ n_persons, int* __restrict__ status) {
+    __shared__ int s_off[1025];
+    if (threadIdx.x == 0) {
+        int o = 0;
+        for (int f = 0; f < F; ++f) { s_off[f] = o; o += min(counts[f], max_persons); }
+        s_off[F] = o;
+        *n_persons = min(o, persons_cap);
+        if (o > persons_cap) atomicOr(status, 2);
+    }
+    __syncthreads();
+    const double dw = (double)(out_w - 1 > 1 ? out_w - 1 : 1), dh = (double)(out_h - 1 > 1 ? out_h - 1 : 1);
+    for (int t = threadIdx.x; t < F * max_persons; t += blockDim.x) {
+        const int f = t / max_persons, i = t % max_persons;
+        if (i >= s_off[f + 1] - s_off[f]) continue;
+        const int p = s_off[f] + i;
+        if (p >= persons_cap) continue;
+        const float* b = boxes_n + (size_t)t * 4;
+        const double y1 = b[0], x1 = b[1], y2 = b[2], x2 = b[3];
+        double* m = M + (size_t)p * 6;
+        m[0] = __ddiv_rn(__dmul_rn(__dsub_rn(x2, x1), (double)(img_w - 1)), dw); m[1] = 0.0; m[2] = __dmul_rn(x1, (double)(img_w - 1));
+        m[3] = 0.0; m[4] = __ddiv_rn(__dmul_rn(__dsub_rn(y2, y1), (double)(img_h - 1)), dh); m[5] = __dmul_rn(y1, (double)(img_h - 1));
+        float* o = boxes + (size_t)p * 4;
+        o[0] = __fmul_rn(b[0], (float)img_h); o[1] = __fmul_rn(b[1], (float)img_w);
+        o[2] = __fmul_rn(b[2], (float)img_h); o[3] = __fmul_rn(b[3], (float)img_w);
+        frame_idx[p] = f;
+        height_cm[p] = heights[min(i, n_heights - 1)];
+    }
+}
+
 }  // namespace
+
+int k_yolo_nms_bounded(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, double iou,
+                       const int* classes, int n_classes, int max_det, int cand_cap, float* out_det, int* out_count,
+                       int* status) {
+    return run_nms_bounded(ctx, pred, B, N, nc, conf, iou, classes, n_classes, max_det, cand_cap, out_det, out_count, status);
+}
+
+int k_persons_from_yolo(hbp_ctx* ctx, const float* det, const int* det_count, int F, int max_det, int in_h, int in_w,
+                        int img_h, int img_w, int out_h, int out_w, const double* heights, int n_heights,
+                        int persons_cap, double* M, float* boxes, int* frame_idx, double* height_cm,
+                        int* n_persons, int* status) {
+    if (F > 1024) { hbp_set_error("at most 1024 frames per call"); return HBP_ERR_INVALID; }
+    const double gain = (double)(in_h > in_w ? in_h : in_w) / (double)(img_h > img_w ? img_h : img_w);
+    const double pad_x = ((double)in_w - (double)img_w * gain) / 2.0, pad_y = ((double)in_h - (double)img_h * gain) / 2.0;
+    persons_from_yolo_kernel<<<1, 256, 0, ctx->stream>>>(det, det_count, F, max_det, (float)pad_x, (float)pad_y, (float)gain,
+                                                        (float)img_w, (float)img_h, out_h, out_w, heights, n_heights,
+                                                        persons_cap, M, boxes, frame_idx, height_cm, n_persons, status);
+    HBP_LAUNCH_CHECK(ctx);
+    return HBP_OK;
+}
+
+int k_persons_from_edet(hbp_ctx* ctx, const float* boxes_n, const int* counts, int F, int max_persons, int img_h,
+                        int img_w, int out_h, int out_w, const double* heights, int n_heights, int persons_cap,
+                        double* M, float* boxes, int* frame_idx, double* height_cm, int* n_persons, int* status) {
+    if (F > 1024) { hbp_set_error("at most 1024 frames per call"); return HBP_ERR_INVALID; }
+    persons_from_edet_kernel<<<1, 256, 0, ctx->stream>>>(boxes_n, counts, F, max_persons, img_h, img_w, out_h, out_w,
+                                                        heights, n_heights, persons_cap, M, boxes, frame_idx, height_cm,
+                                                        n_persons, status);
+    HBP_LAUNCH_CHECK(ctx);
+    return HBP_OK;
+}
 
 int k_yolo_decode_raw(hbp_ctx* ctx, const float* h0, const float* h1, const float* h2, int B, int s0,
                       int s1, int s2, int nc, int in_w, int in_h, float* out) {

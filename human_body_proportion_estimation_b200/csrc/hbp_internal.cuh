@@ -143,17 +143,32 @@ int k_edet_filter(hbp_ctx*, const float* boxes, const float* scores, const float
                   int max_persons, float* out_boxes, int* out_count);
 int k_crop_warp(hbp_ctx*, const uint8_t* frames, int n_frames, int h, int w, const double* M,
                 const int* frame_idx, int P, int out_h, int out_w, int swap_rb, void* out,
-                int out_dtype);
+                int out_dtype, const int* live = nullptr);   // live: optional device count, slots >= *live are skipped
 int k_decode_proportions(hbp_ctx*, const void* hm, int dtype, int P, int J, int Hh, int Wh,
                          const float* boxes, const double* height_cm, const float* thr,
                          int quarter, float* kpts_hm, float* kpts_img, float* scores,
-                         int32_t* idx, uint32_t* ignored, float* lengths, double* torso);
+                         int32_t* idx, uint32_t* ignored, float* lengths, double* torso,
+                         const int* live = nullptr,          // optional device count, slots >= *live are skipped
+                         const double* Maff = nullptr, int crop_h = 0, int crop_w = 0);   // optional (P,6) dst->src matrices: general inverse-affine remap
+int k_yolo_nms_bounded(hbp_ctx*, const float* pred, int B, int N, int nc, float conf, double iou,
+                       const int* classes, int n_classes, int max_det, int cand_cap, float* out_det, int* out_count,
+                       int* status);
+int k_persons_from_yolo(hbp_ctx*, const float* det, const int* det_count, int F, int max_det, int in_h, int in_w,
+                        int img_h, int img_w, int out_h, int out_w, const double* heights, int n_heights,
+                        int persons_cap, double* M, float* boxes, int* frame_idx, double* height_cm,
+                        int* n_persons, int* status);
+int k_persons_from_edet(hbp_ctx*, const float* boxes_n, const int* counts, int F, int max_persons, int img_h,
+                        int img_w, int out_h, int out_w, const double* heights, int n_heights, int persons_cap,
+                        double* M, float* boxes, int* frame_idx, double* height_cm, int* n_persons, int* status);
 // hrnet.cu
 int hrnet_load(hbp_ctx*, int width, int in_h, int in_w, const void* w16, size_t nw,
                const float* bias, size_t nb);
 int hrnet_forward(hbp_ctx*, const __half* crops_dev, int P, void* heatmaps_dev, int out_dtype);
 int hrnet_set_engine(hbp_ctx*, int engine);
 int hrnet_debug_tensor(hbp_ctx*, int id, void* out_host, size_t max_bytes, int* n, int* h, int* w, int* c);
+int hrnet_forward_until(hbp_ctx*, const __half* crops_dev, int P, int stop_after);
+int hrnet_op_count(hbp_ctx*);
+const char* hrnet_op_name(hbp_ctx*, int id);
 void hrnet_free(hbp_ctx*);
 void hrnet_dims(hbp_ctx*, int* in_h, int* in_w, int* width);
 int hrnet_single_conv(hbp_ctx* ctx, int engine, const __half* in, int P, int H, int W, int Cin,

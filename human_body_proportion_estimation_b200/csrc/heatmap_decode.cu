@@ -143,10 +143,12 @@ decode_proportions_kernel(const T* __restrict__ hm, int P, int J, int Hh, int Wh
                           float* __restrict__ kpts_hm, float* __restrict__ kpts_img,
                           float* __restrict__ scores, int32_t* __restrict__ idx_out,
                           uint32_t* __restrict__ ignored_out, float* __restrict__ lengths,
-                          double* __restrict__ torso) {
+                          double* __restrict__ torso, const int* __restrict__ live, const double* __restrict__ Maff,
+                          int crop_h, int crop_w) {
     __shared__ float s_x[kMaxJ], s_y[kMaxJ], s_v[kMaxJ];
     __shared__ int s_i[kMaxJ];
     const int p = blockIdx.x;
+    if (live && p >= *live) return;                     // chained pipeline: person slots beyond the device-side count
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = Hh * Wh;
     for (int j = warp; j < J; j += kWarps) {
@@ -195,6 +197,17 @@ decode_proportions_kernel(const T* __restrict__ hm, int P, int J, int Hh, int Wh
     const float cw = (float)(x2 - x1), ch = (float)(y2 - y1);
     float ix = __fadd_rn(__fmul_rn(__fdiv_rn(x, (float)Wh), cw), (float)x1);
     float iy = __fadd_rn(__fmul_rn(__fdiv_rn(y, (float)Hh), ch), (float)y1);
+    if (Maff) {
+        // optional general inverse affine (north_star item 5): the crop's own dst->src matrix (what hbp_crop_warp sampled
+        // with, rotation / aspect padding included) applied to the heatmap cell's crop coordinate
+        // (u,v) = (x*crop_w/Wh, y*crop_h/Hh), in double, rounded once to float32.  The reference's box formula above stays
+        // the default.
+        const double* m = Maff + (size_t)p * 6;
+        const double u = __ddiv_rn(__dmul_rn((double)x, (double)crop_w), (double)Wh);
+        const double v = __ddiv_rn(__dmul_rn((double)y, (double)crop_h), (double)Hh);
+        ix = (float)__dadd_rn(__dadd_rn(__dmul_rn(m[0], u), __dmul_rn(m[1], v)), m[2]);
+        iy = (float)__dadd_rn(__dadd_rn(__dmul_rn(m[3], u), __dmul_rn(m[4], v)), m[5]);
+    }
     if (have_j && kpts_img) {
         const size_t o = (size_t)p * J + lane;
         kpts_img[2 * o] = ix; kpts_img[2 * o + 1] = iy;
@@ -246,16 +259,17 @@ decode_proportions_kernel(const T* __restrict__ hm, int P, int J, int Hh, int Wh
 int k_decode_proportions(hbp_ctx* ctx, const void* hm, int dtype, int P, int J, int Hh, int Wh,
                          const float* boxes, const double* height_cm, const float* thr, int quarter,
                          float* kpts_hm, float* kpts_img, float* scores, int32_t* idx,
-                         uint32_t* ignored, float* lengths, double* torso) {
+                         uint32_t* ignored, float* lengths, double* torso, const int* live, const double* Maff,
+                         int crop_h, int crop_w) {
     if (P <= 0) return HBP_OK;
     if (dtype == HBP_F32)
         decode_proportions_kernel<float><<<P, kThreads, 0, ctx->stream>>>(
             (const float*)hm, P, J, Hh, Wh, boxes, height_cm, thr, quarter, kpts_hm, kpts_img, scores,
-            idx, ignored, lengths, torso);
+            idx, ignored, lengths, torso, live, Maff, crop_h, crop_w);
     else
         decode_proportions_kernel<__half><<<P, kThreads, 0, ctx->stream>>>(
             (const __half*)hm, P, J, Hh, Wh, boxes, height_cm, thr, quarter, kpts_hm, kpts_img, scores,
-            idx, ignored, lengths, torso);
+            idx, ignored, lengths, torso, live, Maff, crop_h, crop_w);
     HBP_LAUNCH_CHECK(ctx);
     return HBP_OK;
 }

@@ -899,7 +899,7 @@ static int join_all(hbp_ctx* ctx, HrnetModel* m) {
 }
 
 static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, void* heatmaps, int out_dtype,
-                     uint64_t* n_launch) {
+                     uint64_t* n_launch, int stop_after = -1) {
     // fork: side streams join the origin stream (required for capture)
     HBP_CUDA(cudaEventRecord(m->ev_fork, ctx->stream));
     for (int s = 1; s < kStreams; ++s) HBP_CUDA(cudaStreamWaitEvent(stream_of(ctx, m, s), m->ev_fork, 0));
@@ -1019,6 +1019,7 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
         if (timing) cudaEventRecord(tev[2 * i + 1], st);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return hbp_cuda_fail(e, op.name.c_str(), __FILE__, __LINE__);
+        if (stop_after >= 0 && (int)i >= stop_after) break;      // parity hook (hrnet_forward_until)
     }
     if (timing) {
         cudaDeviceSynchronize();
@@ -1107,6 +1108,34 @@ int hrnet_forward(hbp_ctx* ctx, const __half* crops, int P, void* heatmaps, int 
     m->graph_P = P; m->graph_dtype = out_dtype; m->graph_in = crops; m->graph_out = heatmaps;
     m->graph_engine = m->engine;
     return HBP_OK;
+}
+
+// Parity hook: run the program eagerly (no graph) up to and including op `stop_after`, so that the tensors
+// live at that point (e.g. all outputs of a stage module when `stop_after` is the module's last op) can be read
+// with hrnet_debug_tensor before later ops reuse their buffers.  Same plans and kernels as the graph path.
+int hrnet_forward_until(hbp_ctx* ctx, const __half* crops, int P, int stop_after) {
+    HrnetModel* m = ctx->hrnet;
+    if (!m) { hbp_set_error("no model loaded"); return HBP_ERR_STATE; }
+    if (stop_after < 0 || stop_after >= (int)m->ops.size()) { hbp_set_error("bad op index"); return HBP_ERR_INVALID; }
+    if (m->ops[stop_after].kind == OP_HEAD) { hbp_set_error("the head writes the caller's heatmaps: use hbp_hrnet_forward"); return HBP_ERR_INVALID; }
+    int s = ensure_batch(ctx, m, P);
+    if (s) return s;
+    uint64_t n = 0;
+    s = issue_ops(ctx, m, crops, P, nullptr, HBP_F16, &n, stop_after);
+    if (s) return s;
+    ctx->launches += n;
+    HBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < kStreams - 1; ++i) if (m->side[i]) HBP_CUDA(cudaStreamSynchronize(m->side[i]));
+    m->graph_P = P;          // hrnet_debug_tensor sizes its copy by the batch of the last forward
+    m->graph_in = nullptr;   // (never equal to a caller pointer: the next hbp_hrnet_forward runs eagerly once, then re-captures)
+    return HBP_OK;
+}
+
+int hrnet_op_count(hbp_ctx* ctx) { return ctx->hrnet ? (int)ctx->hrnet->ops.size() : 0; }
+const char* hrnet_op_name(hbp_ctx* ctx, int id) {
+    HrnetModel* m = ctx->hrnet;
+    if (!m || id < 0 || id >= (int)m->ops.size()) return nullptr;
+    return m->ops[id].name.c_str();
 }
 
 int hrnet_debug_tensor(hbp_ctx* ctx, int id, void* out_host, size_t max_bytes, int* n, int* h, int* w, int* c) {

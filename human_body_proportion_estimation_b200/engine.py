@@ -138,6 +138,13 @@ class Engine:
     def yolo_nms_legacy(self, pred, num_classes, conf_thres=0.5, nms_thres=0.4, max_out=None):
         pred = _c(pred, np.float32)
         B, N, E = pred.shape
+        num_classes = int(num_classes)
+        # the reference slices the class scores [:, 5:5+num_classes] (onnx_utils.py:59): rows may be wider than
+        # 5+num_classes (extra columns ignored) but never narrower; the C side strides rows by 5+nc
+        if num_classes < 1 or E < 5 + num_classes:
+            raise ValueError("prediction rows have %d columns, need at least 5 + num_classes = %d" % (E, 5 + num_classes))
+        if E > 5 + num_classes:
+            pred = np.ascontiguousarray(pred[..., :5 + num_classes])
         max_out = max_out or N
         det = np.zeros((B, max_out, 7), np.float32)
         cnt = np.zeros((B,), np.int32)
@@ -222,6 +229,29 @@ class Engine:
         hm = np.empty((P, 17, ih // 4, iw // 4), out_dtype)
         check(self._lib.hbp_hrnet_forward(self._ctx, ptr(crops), P, ptr(hm), _NP2HBP[np.dtype(out_dtype)], HOST))
         return hm
+
+    # parity hooks (per-stage error attribution against the fp32 oracle)
+    def hrnet_op_names(self):
+        n = C.c_int()
+        check(self._lib.hbp_hrnet_op_name(self._ctx, 0, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(256)
+        names = []
+        for i in range(n.value):
+            check(self._lib.hbp_hrnet_op_name(self._ctx, i, buf, 256, None))
+            names.append(buf.value.decode())
+        return names
+
+    def hrnet_forward_until(self, crops, op_index):
+        crops = _c(crops, np.float16)
+        check(self._lib.hbp_hrnet_forward_until(self._ctx, ptr(crops), crops.shape[0], int(op_index), HOST))
+
+    def hrnet_debug_tensor(self, op_index):
+        """output tensor of program op `op_index` after the last forward: (P,h,w,c) fp16 NHWC (c as stored)"""
+        n, h, w, c = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(self._lib.hbp_hrnet_debug_tensor(self._ctx, int(op_index), None, 0, C.byref(n), C.byref(h), C.byref(w), C.byref(c)))
+        out = np.empty((n.value, h.value, w.value, c.value), np.float16)
+        check(self._lib.hbp_hrnet_debug_tensor(self._ctx, int(op_index), ptr(out), out.nbytes, None, None, None, None))
+        return out
 
     # ---- K6 ----------------------------------------------------------------
     def decode_proportions(self, heatmaps, boxes_yxyx_px=None, height_cm=None,

@@ -160,8 +160,8 @@ HBP_API int hbp_crop_warp(hbp_ctx* ctx, const uint8_t* frames, int n_frames, int
  * Replaces the opaque network behind hble/modules/pose_estimator.py:47-59
  * (onnxruntime) and the Triton `hrnet` model of the ensemble
  * (hble/person_det_pose_edet4_trtserver.py:22-23).  Weights: BN-folded fp16
- * blob in the layer order of hbp_hrnet_layer_table (see the Python package's
- * hrnet_arch.py).  width 32|48; in_h,in_w multiples of 32 (256x192, 384x288). */
+ * blob in the layer order of hbp_hrnet_describe (below; the Python package's
+ * hrnet_arch.py fills it).  width 32|48; in_h,in_w multiples of 32 (256x192, 384x288). */
 HBP_API int hbp_hrnet_load(hbp_ctx* ctx, int width, int in_h, int in_w,
                    const void* weights_f16, size_t n_weight_halfs,
                    const float* biases_f32, size_t n_biases);
@@ -196,9 +196,18 @@ HBP_API int hbp_conv2d_nhwc_timed(hbp_ctx* ctx, int engine, const void* in_f16, 
 /* which conv engine the loaded model runs: 0 = SIMT direct conv,
  * 1 = tcgen05/TMEM implicit GEMM fed by TMA. */
 HBP_API int hbp_hrnet_set_engine(hbp_ctx* ctx, int engine);
-/* debug/parity hook: copy an intermediate activation (NHWC fp16) to the host */
-HBP_API int hbp_hrnet_debug_tensor(hbp_ctx* ctx, int tensor_id, void* out_host, size_t max_bytes,
+/* debug/parity hooks (tests/test_gpu_hrnet_parity.py: per-stage error attribution against the fp32 oracle).
+ * hbp_hrnet_debug_tensor copies the output tensor of program op `op_index` (NHWC fp16, channels as stored:
+ * W48's 48/96-channel tensors are padded to 64/128) to the host; buffers are reused along the program, so a
+ * tensor is only intact while it is live -- hbp_hrnet_forward_until runs the program eagerly (same plans and
+ * kernels as the CUDA-graph path) up to and including op `op_index` and stops there.  hbp_hrnet_op_name
+ * enumerates the program: *n_ops = number of ops, buf = name of op `op_index` (public HRNet state_dict prefixes
+ * for convolutions; "<module>.fuse_levelK" / "<module>.fuse_upaddK" / "<module>.fuse_layers.I.upadd" for the
+ * grouped launches and the upsample-adds). */
+HBP_API int hbp_hrnet_debug_tensor(hbp_ctx* ctx, int op_index, void* out_host, size_t max_bytes,
                            int* n, int* h, int* w, int* c);
+HBP_API int hbp_hrnet_forward_until(hbp_ctx* ctx, const void* crops_f16, int P, int op_index, int mem);
+HBP_API int hbp_hrnet_op_name(hbp_ctx* ctx, int op_index, char* buf, size_t buf_bytes, int* n_ops);
 
 /* ---- K6: heatmap decode fused with body-proportion geometry -------------- *
  * Replaces hble/modules/pose_estimator.py:74-99 (argmax decode),

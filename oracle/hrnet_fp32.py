@@ -64,20 +64,32 @@ class HRNetFP32:
         return outs
 
     @torch.no_grad()
-    def forward(self, x, return_features=False):
+    def forward(self, x, return_features=False, stages=None):
+        """stages: optional dict that receives the activations at the stage boundaries, NCHW fp32:
+        "conv2", "layer1", "transition1.{0,1}", "<module>.<branch>" for every HighResolutionModule output."""
+        keep = (lambda k, t: stages.__setitem__(k, t.numpy().copy())) if stages is not None else (lambda k, t: None)
         x = torch.as_tensor(x).float()
         x = self.cv("conv1", x, stride=2)
         x = self.cv("conv2", x, stride=2)
+        keep("conv2", x)
         for b in range(4):
             x = self.bottleneck("layer1.%d" % b, x, project=(b == 0))
+        keep("layer1", x)
         xs = [self.cv("transition1.0.0", x), self.cv("transition1.1.0.0", x, stride=2)]
+        keep("transition1.0", xs[0]); keep("transition1.1", xs[1])
         xs = self.module("stage2.0", xs)
+        for i, t in enumerate(xs):
+            keep("stage2.0.%d" % i, t)
         xs.append(self.cv("transition2.2.0.0", xs[-1], stride=2))
         for m in range(4):
             xs = self.module("stage3.%d" % m, xs)
+            for i, t in enumerate(xs):
+                keep("stage3.%d.%d" % (m, i), t)
         xs.append(self.cv("transition3.3.0.0", xs[-1], stride=2))
         for m in range(3):
             xs = self.module("stage4.%d" % m, xs, multi_scale=(m < 2))
+            for i, t in enumerate(xs):
+                keep("stage4.%d.%d" % (m, i), t)
         hm = self.cv("final_layer", xs[0], relu=False)
         if return_features:
             return hm, xs[0]

@@ -36,12 +36,18 @@ def main():
         if os.environ.get("HBP_MB_NORES"):
             use_res = False
         res = rng.standard_normal((P, H // s * up, W // s * up, Cout)).astype(np.float16) if use_res else None
-        _, used, ms = eng.conv2d_nhwc(x, w, b, res, s, up, True, engine, time_iters=int(os.environ.get("HBP_MB_ITERS", "50")))
+        iters = int(os.environ.get("HBP_MB_ITERS", "50"))
+        r = eng.conv2d_nhwc(x, w, b, res, s, up, True, engine, time_iters=iters)
+        if iters <= 0:            # HBP_CONV_TRACE runs: plan + per-CTA phase trace on stderr only
+            continue
+        _, used, ms = r
         flop = 2.0 * P * (H // s) * (W // s) * Cin * Cout * k * k
         rows.append(dict(shape=[H, W, Cin, Cout, k, s, up], engine=used, us=ms * 1e3, tflops=flop / ms / 1e9,
                          share_pct=share))
         print("%-34s eng=%d %8.2f us %8.1f TFLOP/s  (%.1f %% of W32 FLOPs)" %
               ((H, W, Cin, Cout, k, s, up), used, ms * 1e3, flop / ms / 1e9, share), flush=True)
+    if not rows:
+        return
     tot = sum(r["share_pct"] for r in rows)
     t = sum(r["share_pct"] / r["tflops"] for r in rows)
     print("FLOP-weighted harmonic mean over %.1f %% of the network: %.1f TFLOP/s" % (tot, tot / t))
