@@ -29,6 +29,17 @@ class PipelineParams(C.Structure):
                 ("swap_rb", C.c_int), ("quarter_offset", C.c_int), ("heatmap_dtype", C.c_int)]
 
 
+class DetPoseParams(C.Structure):
+    _fields_ = [("n_frames", C.c_int), ("h", C.c_int), ("w", C.c_int), ("detector", C.c_int), ("persons_cap", C.c_int),
+                ("swap_rb", C.c_int), ("quarter_offset", C.c_int), ("person_class", C.c_int),
+                ("N", C.c_int), ("nc", C.c_int), ("in_h", C.c_int), ("in_w", C.c_int), ("letterbox_mode", C.c_int),
+                ("max_det", C.c_int), ("cand_cap", C.c_int), ("conf_thres", C.c_float), ("iou_thres", C.c_double),
+                ("K", C.c_int), ("max_persons", C.c_int), ("det_thres", C.c_float), ("x_expand", C.c_float),
+                ("y_expand", C.c_float), ("mem", C.c_int)]
+
+
+DET_YOLO, DET_EDET = 0, 1
+
 _P = C.c_void_p
 _I = C.c_int
 _SIGS = {
@@ -72,6 +83,10 @@ _SIGS = {
     "hbp_hrnet_op_name": (_I, [_P, _I, C.c_char_p, C.c_size_t, C.POINTER(_I)]),
     "hbp_decode_proportions": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P,
                                     _P, _P, _I]),
+    "hbp_decode_proportions_affine": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P,
+                                           _P, _P, _I]),
+    "hbp_det_pose_submit": (_I, [_P, C.POINTER(DetPoseParams), _P, _P, _P, _P, _P, _I, _P, C.POINTER(_I)]),
+    "hbp_det_pose_collect": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I), _P, _P, _P, _P, _P, _P, _P, _P]),
     "hbp_pose_pipeline": (_I, [_P, C.POINTER(PipelineParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                _P, _P]),
     "hbp_pose_pipeline_submit": (_I, [_P, C.POINTER(PipelineParams), _P, _P, _P, _P, _P, _P, C.POINTER(_I)]),

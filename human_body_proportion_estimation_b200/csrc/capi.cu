@@ -399,10 +399,32 @@ int hbp_hrnet_op_name(hbp_ctx* ctx, int op_index, char* buf, size_t buf_bytes, i
     return HBP_OK;
 }
 
+static int decode_impl(hbp_ctx* ctx, const void* hm, int dtype, int P, int J, int Hh, int Wh,
+                       const float* boxes, const double* M, int crop_h, int crop_w, const double* height_cm, const float* thr, int quarter,
+                       float* kpts_hm, float* kpts_img, float* scores, int32_t* idx,
+                       uint32_t* ignored, float* lengths, double* torso, int mem);
+
 int hbp_decode_proportions(hbp_ctx* ctx, const void* hm, int dtype, int P, int J, int Hh, int Wh,
                            const float* boxes, const double* height_cm, const float* thr, int quarter,
                            float* kpts_hm, float* kpts_img, float* scores, int32_t* idx,
                            uint32_t* ignored, float* lengths, double* torso, int mem) {
+    return decode_impl(ctx, hm, dtype, P, J, Hh, Wh, boxes, nullptr, 0, 0, height_cm, thr, quarter, kpts_hm, kpts_img, scores, idx,
+                       ignored, lengths, torso, mem);
+}
+
+int hbp_decode_proportions_affine(hbp_ctx* ctx, const void* hm, int dtype, int P, int J, int Hh, int Wh,
+                                  const float* boxes, const double* M, int crop_h, int crop_w, const double* height_cm,
+                                  const float* thr, int quarter, float* kpts_hm, float* kpts_img, float* scores, int32_t* idx,
+                                  uint32_t* ignored, float* lengths, double* torso, int mem) {
+    if (!M || !boxes || crop_h <= 0 || crop_w <= 0) { hbp_set_error("hbp_decode_proportions_affine: M, boxes and the crop size are required"); return HBP_ERR_INVALID; }
+    return decode_impl(ctx, hm, dtype, P, J, Hh, Wh, boxes, M, crop_h, crop_w, height_cm, thr, quarter, kpts_hm, kpts_img, scores, idx,
+                       ignored, lengths, torso, mem);
+}
+
+static int decode_impl(hbp_ctx* ctx, const void* hm, int dtype, int P, int J, int Hh, int Wh,
+                       const float* boxes, const double* M, int crop_h, int crop_w, const double* height_cm, const float* thr, int quarter,
+                       float* kpts_hm, float* kpts_img, float* scores, int32_t* idx,
+                       uint32_t* ignored, float* lengths, double* torso, int mem) {
     BIND(ctx);
     HBP_REQUIRE(hm && P >= 0 && J > 0 && J <= 32 && Hh > 0 && Wh > 0, "bad shape");
     HBP_REQUIRE(dtype == HBP_F32 || dtype == HBP_F16, "heatmaps must be f32 or f16");
@@ -417,6 +439,7 @@ int hbp_decode_proportions(hbp_ctx* ctx, const void* hm, int dtype, int P, int J
     const float* db = st.in(boxes, (size_t)P * 4, SC_IN1);
     const double* dh = st.in(height_cm, (size_t)P, SC_IN2);
     const float* dt = st.in(thr, (size_t)J, SC_IN3);
+    const double* dM = st.in(M, (size_t)P * 6, SC_IN4);
     float* o_hm = st.out(kpts_hm, (size_t)P * J * 2, SC_OUT0);
     float* o_img = st.out(kpts_img, (size_t)P * J * 2, SC_OUT1);
     float* o_sc = st.out(scores, (size_t)P * J, SC_OUT2);
@@ -426,7 +449,7 @@ int hbp_decode_proportions(hbp_ctx* ctx, const void* hm, int dtype, int P, int J
     double* o_to = st.out(torso, (size_t)P, SC_OUT6);
     if (st.status) return st.status;
     int s = k_decode_proportions(ctx, dhm, dtype, P, J, Hh, Wh, db, dh, dt, quarter, o_hm, o_img, o_sc,
-                                 o_idx, o_ig, o_len, o_to);
+                                 o_idx, o_ig, o_len, o_to, nullptr, dM, crop_h, crop_w);
     if (s) return s;
     st.back(kpts_hm, o_hm, (size_t)P * J * 2);
     st.back(kpts_img, o_img, (size_t)P * J * 2);
@@ -620,7 +643,7 @@ int hbp_pose_pipeline_collect(hbp_ctx* ctx, int ticket, float* kpts_img, float* 
     BIND(ctx);
     HBP_REQUIRE(ticket >= 0 && ticket < HBP_PIPE_SLOTS, "bad ticket");
     hbp_pipe_slot& sl = ctx->pipe[ticket];
-    if (!sl.busy) { hbp_set_error("ticket %d has nothing in flight", ticket); return HBP_ERR_STATE; }
+    if (!sl.busy || sl.det_pose) { hbp_set_error("ticket %d has no pose batch in flight", ticket); return HBP_ERR_STATE; }
     if (sl.P == 0) { sl.busy = false; return HBP_OK; }
     HBP_CUDA(cudaEventSynchronize(sl.ev_done));
     const int P = sl.P, J = 17;

@@ -77,6 +77,7 @@ struct ConvParams {
     int issuers;                 // halo mode: MMA-issuing warps
     int teams;                   // halo mode: epilogue teams (2 needs an even number of ring stages and accumulator buffers) (2: alternate tiles, one accumulator buffer each)
     int phase_maps;              // stride-2 per-tap mode: the four (row, column) parity planes of the input have their own dense tensor maps
+    int b_sets;                  // chain kernel, resident weights: 1 = one set reloaded at every layer switch, 2 = the next layer's set is prefetched
     int bias_mma;                // halo mode: the bias enters the accumulator through one extra MMA per M-tile (ones x [bias_hi, bias_lo]) instead of the epilogue
     int res_mma;                 // halo mode: the residual tile (TMA ring) is added by MMAs against a 32x32 identity instead of the epilogue
     uint32_t c_bytes;            // halo mode: constant operand tiles (ones, identity, bias) between the residual ring and the barriers
@@ -1214,6 +1215,545 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (p.tl && threadIdx.x == 0) atomicMax(p.tl + 1, globaltimer_ns());
 }
 
+
+// ---------------------------------------------------------------------------
+// Chain kernel: the 3x3 stride-1 convolutions of one resolution branch of a stage module (4 BasicBlocks = 8
+// convolutions, same tensor shape throughout) as ONE persistent launch.  A kernel boundary between two dependent
+// convolutions costs ~6.7 us at batch 64 (launch gap, prologue, first halo tile / weights, drain of the last tile:
+// profiles/r02_branch_conv_slope.md) around 6 us of steady-state work -- but images are independent, so layer l+1 of
+// a tile only needs layer l of the SAME image's neighbouring tiles.  Here every CTA owns a contiguous range of tiles
+// (the same range in every layer) and walks layer 0, layer 1, ... over it; a tile's halo load waits for per-tile
+// completion flags of the (up to nine) tiles of the previous layer it reads, written by whichever CTA owns them:
+//   epilogue warp after its stores:  fence.proxy.async (generic writes -> TMA reads) ; __threadfence ; red.release.gpu +1
+//   producer warp before the load :  ld.acquire.gpu until the flag shows 4 arrivals of this launch ; fence.proxy.async
+// All CTAs of the launch are co-resident (grid <= SMs of the branch's share, one CTA per SM), dependencies only point
+// to earlier layers, every CTA walks the layers in order: no deadlock.  Inside a CTA the walk starts at the first
+// image boundary of its range, so that the first tiles of a layer read tiles the neighbour CTAs finished a whole
+// layer earlier; the TMA ring, the TMEM double buffering and the epilogue teams run on across layer boundaries.
+// Flags count arrivals over all launches (4 per tile and launch); the launch number comes from a device counter that
+// the last CTA to leave increments, so graph replays need no memset node.
+// Weights: resident set reloaded slot by slot at a layer switch (each issuer releases a slot after its last tile of
+// the layer), or the streaming ring, which simply runs on into the next layer's weights.  Activation buffers may be
+// reused two layers later (the program's own liveness pool does that): tile (l+2, t) starts only after every tile
+// that read region t of the old contents has finished.
+constexpr int kMaxChain = 8;
+struct alignas(64) ChainEntry {
+    CUtensorMap tmA, tmB, tmR;
+    const float* bias;
+    __half* out;
+    int relu, has_res;
+    int res_layer;               // layer of this chain whose output is the residual (-1: a tensor written before the launch)
+    unsigned long long* tl;      // HBP_TIMELINE stamps of this member op
+};
+struct ChainHeader {
+    int n_layers;
+    unsigned* flags;             // [n_layers][n_tiles] arrival counters
+    unsigned* state;             // [0] launches completed, [1] CTAs that have left the current launch
+    unsigned long long* trace;   // bring-up (HBP_CHAIN_TRACE=<op name substring>): [cta][layer][first tile start, last tile end] globaltimer ns
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+constexpr int kMaxChainTiles = 512;          // tiles per CTA and layer the chain kernel's shared tables hold
+struct ChainTile {                           // one tile of this CTA's walk, by position
+    uint32_t tile;                           // global tile index
+    uint32_t origin;                         // element offset of the tile's first output pixel, channel 0
+    uint16_t n0, tg;                         // first image, image-group index
+    uint8_t tw, th, outer, pad;              // tile column / row; outer: some other CTA's halo reads this tile
+};
+struct ChainLayer {
+    __half* out;
+    unsigned long long* tl;
+    int relu, has_res, res_layer;
+};
+
+template <int KSTEPS, int MT>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_umma_chain_kernel(const ChainEntry* __restrict__ table, const ConvParams p, const ChainHeader hdr) {
+    constexpr int KS = 3, HW = kHaloW;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ ChainTile s_tile[kMaxChainTiles];           // by walk position q
+    __shared__ unsigned s_done[kMaxChainTiles];            // by local tile index: arrivals (4 per finished layer) of this launch
+    __shared__ unsigned short s_pos[kMaxChainTiles];       // scratch of the order computation
+    __shared__ ChainLayer s_layer[kMaxChain];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_tile_bytes = p.n_chunks * p.a_chunk_bytes;
+    const uint32_t a_base = smem_base;
+    const uint32_t b_base = a_base + p.a_stages * a_tile_bytes;
+    const uint32_t r_base = b_base + p.b_slots * (uint32_t)KS * p.b_stage_bytes;
+    const uint32_t r_tile_bytes = p.res_smem ? p.r_chunks * p.r_chunk_bytes : 0u;
+    const uint32_t bar_base = r_base + p.a_stages * r_tile_bytes;
+    const uint32_t a_full = bar_base;                                   // a_stages x n_chunks
+    const uint32_t a_empty = a_full + 8u * (kMaxAStages * kMaxChunks);  // a_stages
+    const uint32_t b_full = a_empty + 8u * kMaxAStages;                 // b_slots
+    const uint32_t b_empty = b_full + 8u * kMaxBSlots;                  // b_slots
+    const uint32_t acc_full = b_empty + 8u * kMaxBSlots;                // acc_bufs
+    const uint32_t acc_empty = acc_full + 8u * kMaxAccBufs;             // acc_bufs
+    const uint32_t res_full = acc_empty + 8u * kMaxAccBufs;             // a_stages
+    const uint32_t res_empty = res_full + 8u * kMaxAStages;             // a_stages
+    const uint32_t tmem_slot = res_empty + 8u * kMaxAStages;
+    float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + kHaloBarBytes - smem_u32(smem_raw)));   // [layer][n_tile]
+
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    const int L = hdr.n_layers;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    // this CTA's tiles: [t0, t0 + T) in every layer
+    const int t0 = (int)(((long long)blockIdx.x * p.n_tiles) / (long long)gridDim.x);
+    const int T = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / (long long)gridDim.x) - t0;
+    const int total = L * T;                                             // tile sequence numbers s = l * T + q
+    const int n_slots = KS * p.n_chunks;                                 // weight slots per layer: (chunk, dx), three taps each
+
+    pdl_launch_dependents();
+    // Walk order inside a layer: first the tiles some OTHER CTA's halo reads (a neighbour tile outside [t0, t0+T)), then the
+    // rest in index order.  What a neighbour CTA needs of layer l is then published early in its pass over layer l, and what
+    // this CTA needs of its own interior was finished most of a layer ago: no CTA waits at a layer boundary.
+    for (int i = threadIdx.x; i < T; i += kHaloThreads) {
+        const int tile = t0 + i;
+        const int tw = tile % p.tiles_w, th_ = (tile / p.tiles_w) % p.tiles_h, tg = tile / tiles_per_img;
+        bool outer = false;
+        for (int dh = -1; dh <= 1; ++dh)
+            for (int dw = -1; dw <= 1; ++dw) {
+                const int nh = th_ + dh, nw = tw + dw;
+                if (nh < 0 || nh >= p.tiles_h || nw < 0 || nw >= p.tiles_w) continue;
+                const int nt = (tg * p.tiles_h + nh) * p.tiles_w + nw;
+                outer = outer || nt < t0 || nt >= t0 + T;
+            }
+        if (p.dbg_flags & 32) outer = false;
+        s_pos[i] = outer ? 1 : 0;
+        s_done[i] = 0u;
+    }
+    if ((int)threadIdx.x < L) {
+        const ChainEntry& e = table[threadIdx.x];
+        ChainLayer li;
+        li.out = e.out; li.tl = e.tl; li.relu = e.relu; li.has_res = e.has_res; li.res_layer = e.res_layer;
+        s_layer[threadIdx.x] = li;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                  // stable partition (T is a few dozen): s_pos[i] <- walk position of local tile i
+        int n_outer = 0;
+        for (int i = 0; i < T; ++i) n_outer += s_pos[i];
+        int a = 0, b = n_outer;
+        for (int i = 0; i < T; ++i) { const bool o = s_pos[i] != 0; s_pos[i] = (unsigned short)((o ? a++ : b++) | (o ? 0x8000 : 0)); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T; i += kHaloThreads) {
+        const int tile = t0 + i;
+        const int tw = tile % p.tiles_w, th_ = (tile / p.tiles_w) % p.tiles_h, tg = tile / tiles_per_img;
+        ChainTile ct;
+        ct.tile = (uint32_t)tile;
+        ct.n0 = (uint16_t)(tg * p.tn); ct.tg = (uint16_t)tg;
+        ct.tw = (uint8_t)tw; ct.th = (uint8_t)th_; ct.outer = (s_pos[i] & 0x8000) ? 1 : 0; ct.pad = 0;
+        ct.origin = (uint32_t)((((size_t)tg * p.tn * p.Ho + (size_t)th_ * p.th) * p.Wo + (size_t)tw * 8) * p.Cout);
+        s_tile[s_pos[i] & 0x7fff] = ct;
+    }
+    if (warp == 0) {
+        for (int i = lane; i < L; i += 32) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&table[i].tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&table[i].tmB) : "memory");
+            if (table[i].has_res) asm volatile("prefetch.tensormap [%0];" ::"l"(&table[i].tmR) : "memory");
+        }
+        for (int i = lane; i < p.a_stages * p.n_chunks; i += 32) mbar_init(a_full + 8u * i, 1);
+        for (int i = lane; i < p.a_stages; i += 32) { mbar_init(a_empty + 8u * i, 1); mbar_init(res_full + 8u * i, 1); mbar_init(res_empty + 8u * i, 4); }
+        for (int i = lane; i < p.b_slots; i += 32) { mbar_init(b_full + 8u * i, 1); mbar_init(b_empty + 8u * i, p.b_resident ? (uint32_t)p.issuers : 1u); }
+        for (int i = lane; i < kMaxAccBufs; i += 32) { mbar_init(acc_full + 8u * i, 1); mbar_init(acc_empty + 8u * i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+    for (int i = threadIdx.x; i < L * p.n_tile; i += kHaloThreads) s_bias[i] = table[i / p.n_tile].bias[i % p.n_tile];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t acc_stride = (uint32_t)(MT * p.n_tile);
+    const uint32_t b_bytes = (uint32_t)p.n_tile * p.row_bytes;
+    const uint32_t b_slot_bytes = (uint32_t)KS * p.b_stage_bytes;
+    // spin with a watchdog: a dependency that never arrives is a bug -- trap instead of hanging the GPU
+    auto spin_guard = [&](unsigned& spins, long long& t_start) {
+        __nanosleep(32);
+        if ((++spins & 4095u) == 0u) {
+            const long long now = clock64();
+            if (t_start == 0) t_start = now;
+            else if (now - t_start > 8000000000LL) __trap();
+        }
+    };
+
+    if (warp == 0) {
+        // ===== producer: halo tiles (after their dependencies) and weights =====
+        auto load_slot = [&](int l, int i, int slot) {      // weight slot i = (chunk, dx) of layer l -> ring / resident slot `slot`
+            const int cc = i / KS, dx = i % KS;
+            if (elect_one()) {
+                mbar_expect_tx(b_full + 8u * slot, (uint32_t)KS * b_bytes);
+                for (int dy = 0; dy < KS; ++dy)
+                    tma_load_2d(b_base + slot * b_slot_bytes + dy * p.b_stage_bytes, &table[l].tmB, b_full + 8u * slot, cc * p.chunk,
+                                (dy * KS + dx) * p.Cout);
+            }
+            __syncwarp();
+        };
+        pdl_wait();
+        const unsigned want = 4u * (*reinterpret_cast<volatile const unsigned*>(hdr.state) + 1u);   // arrivals a finished tile shows in THIS launch
+        int bs = 0;                         // streaming ring position
+        uint32_t bph = 0;
+        for (int s = 0; s < total; ++s) {
+            const int l = s / T, q = s - l * T;
+            const ChainTile ct = s_tile[q];
+            if (l > 0 && !(p.dbg_flags & 4)) {
+                // the (up to nine) tiles of layer l-1 this halo reads: lanes 0..8 check one each -- this CTA's own tiles in
+                // shared memory, the neighbours' through their global flags
+                const int dh = lane / 3 - 1, dw = lane % 3 - 1;
+                const int nh = (int)ct.th + dh, nw = (int)ct.tw + dw;
+                const bool mine = lane < 9 && nh >= 0 && nh < p.tiles_h && nw >= 0 && nw < p.tiles_w;
+                const int nt = ((int)ct.tg * p.tiles_h + (mine ? nh : 0)) * p.tiles_w + (mine ? nw : 0);
+                const int ni = nt - t0;
+                const bool local = ni >= 0 && ni < T;
+                const unsigned* f = hdr.flags + (size_t)(l - 1) * p.n_tiles + nt;
+                const unsigned need_local = 4u * (unsigned)l;
+                unsigned spins = 0;
+                long long t_start = 0;
+                while (true) {
+                    bool ok = true;
+                    if (mine) ok = local ? (*reinterpret_cast<volatile unsigned*>(&s_done[ni]) >= need_local) : (ld_acquire_gpu(f) >= want);
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    spin_guard(spins, t_start);
+                }
+                __threadfence_block();
+                asm volatile("fence.proxy.async;" ::: "memory");   // observed generic-proxy writes -> the TMA reads below
+            }
+            const int sa = s % p.a_stages, lap = s / p.a_stages;
+            if (lap > 0) mbar_wait(a_empty + 8u * sa, (uint32_t)((lap - 1) & 1));
+            if (elect_one()) {
+                const int n0 = ct.n0, h0 = (int)ct.th * p.th, w0 = (int)ct.tw * 8;
+                for (int cc = 0; cc < p.n_chunks; ++cc) {
+                    const uint32_t bar = a_full + 8u * (sa * p.n_chunks + cc);
+                    mbar_expect_tx(bar, p.a_box_bytes);
+                    tma_load_4d(a_base + sa * a_tile_bytes + cc * p.a_chunk_bytes, &table[l].tmA, bar, cc * p.chunk, w0 - 1, h0 - 1, n0);
+                }
+            }
+            __syncwarp();
+            if (!p.b_resident) {
+                // streaming ring: the weights of tile s, slot by slot (runs ahead of the MMA warp by b_slots slots)
+                for (int i = 0; i < n_slots; ++i) {
+                    mbar_wait(b_empty + 8u * bs, bph ^ 1u);
+                    load_slot(l, i, bs);
+                    if (++bs == p.b_slots) { bs = 0; bph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===== residual producer: one ring stage per tile of EVERY layer (layers without a residual complete the stage empty),
+        // so that the ring's phases stay aligned with the tile sequence =====
+        // Resident weights are this warp's job too (the halo producer must never block on them: it runs ahead across the
+        // layer boundary, so the halo ring is full when the new weights land).  Layer lt uses set lt % b_sets; its slots are
+        // free once every issuer has passed its last tile of layer lt - b_sets (each commits b_empty there).
+        auto load_wslot = [&](int l, int i) {
+            const int cc = i / KS, dx = i % KS, slot = (l % p.b_sets) * n_slots + i;
+            if (elect_one()) {
+                mbar_expect_tx(b_full + 8u * slot, (uint32_t)KS * b_bytes);
+                for (int dy = 0; dy < KS; ++dy)
+                    tma_load_2d(b_base + slot * b_slot_bytes + dy * p.b_stage_bytes, &table[l].tmB, b_full + 8u * slot, cc * p.chunk,
+                                (dy * KS + dx) * p.Cout);
+            }
+            __syncwarp();
+        };
+        if (p.b_resident)
+            for (int l = 0; l < p.b_sets && l < L; ++l)
+                for (int i = 0; i < n_slots; ++i) load_wslot(l, i);           // weights do not depend on the previous launch
+        if (p.res_smem || p.b_resident) {
+            pdl_wait();
+            for (int s = 0; s < total; ++s) {
+                const int l = s / T, q = s - l * T;
+                if (p.b_resident && q == 0 && l > 0) {
+                    const int lt = l + p.b_sets - 1;
+                    if (lt < L)
+                        for (int i = 0; i < n_slots; ++i) {
+                            mbar_wait(b_empty + 8u * ((lt % p.b_sets) * n_slots + i), (uint32_t)((lt / p.b_sets - 1) & 1));
+                            load_wslot(lt, i);
+                        }
+                }
+                if (!p.res_smem) continue;
+                const ChainTile ct = s_tile[q];
+                const ChainLayer li = s_layer[l];
+                const int sr = s % p.a_stages, lap = s / p.a_stages;
+                if (lap > 0) mbar_wait(res_empty + 8u * sr, (uint32_t)((lap - 1) & 1));
+                // the residual of layer l is the output of an earlier layer of this chain (same tile: written by this CTA's own
+                // epilogue, normally a whole layer ago) or a tensor from before the launch
+                if (li.has_res && li.res_layer >= 0 && !(p.dbg_flags & 4)) {
+                    const unsigned need = 4u * (unsigned)(li.res_layer + 1);
+                    const volatile unsigned* d = &s_done[(int)ct.tile - t0];
+                    unsigned spins = 0;
+                    long long t_start = 0;
+                    while (*d < need) spin_guard(spins, t_start);
+                    __threadfence_block();
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                if (elect_one()) {
+                    if (li.has_res) {
+                        mbar_expect_tx(res_full + 8u * sr, (uint32_t)p.r_chunks * p.r_box_bytes);
+                        for (int rc = 0; rc < p.r_chunks; ++rc)
+                            tma_load_4d(r_base + sr * r_tile_bytes + rc * p.r_chunk_bytes, &table[l].tmR, res_full + 8u * sr, rc * 64,
+                                        (int)ct.tw * 8, (int)ct.th * p.th, ct.n0);
+                    } else {
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(res_full + 8u * sr) : "memory");
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp <= 2) {
+      if (warp - 1 < p.issuers) {
+        // ===== MMA issuers: tile s by warp s % issuers into accumulator buffer s % acc_bufs =====
+        const int iss = warp - 1;
+        constexpr uint32_t kRow16 = KSTEPS * 2;
+        constexpr uint32_t kMtStep = 16u * HW * kRow16;
+        const uint64_t da0 = make_desc(0, p.row_bytes, HW * p.row_bytes);
+        const uint64_t db0 = make_desc(0, p.row_bytes);
+        const uint32_t bstep = p.b_stage_bytes >> 4;
+        const uint32_t idesc = p.idesc, n_tile = (uint32_t)p.n_tile;
+        int bs = 0;                         // streaming ring position (one issuer in that mode)
+        uint32_t bph = 0;
+        int seen_layer = -1;                // resident weights: layer whose slots this warp has already waited for
+        for (int s = iss; s < total; s += p.issuers) {
+            const int l = s / T;
+            const int sa = s % p.a_stages, lap_a = s / p.a_stages;
+            const int ab = s % p.acc_bufs, use = s / p.acc_bufs;
+            const uint32_t pa = (uint32_t)(lap_a & 1);
+            if (use > 0) {
+                mbar_wait(acc_empty + 8u * ab, (uint32_t)((use - 1) & 1));
+                tc_fence_after();
+            }
+            const uint32_t d_base = tmem_base + ab * acc_stride;
+            const bool last_of_layer = p.b_resident && s + p.issuers >= (l + 1) * T && l + p.b_sets < L;   // my last tile of layer l: release its slots to layer l + b_sets
+            const bool fast = p.b_resident && seen_layer == l && !last_of_layer;
+            const int set0 = p.b_resident ? (l % p.b_sets) * n_slots : 0;
+            for (int cc = 0; cc < p.n_chunks; ++cc) {
+                mbar_wait(a_full + 8u * (sa * p.n_chunks + cc), pa);
+                const uint64_t a_c = da0 + ((a_base + sa * a_tile_bytes + cc * p.a_chunk_bytes) >> 4);
+                if (fast) {
+                    tc_fence_after();
+                    const uint64_t b_c = db0 + ((b_base + (uint32_t)(set0 + cc * KS) * b_slot_bytes) >> 4);
+                    const uint32_t fresh = cc == 0 ? 0u : 1u;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int dx = 0; dx < KS; ++dx)
+#pragma unroll
+                            for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+                                for (int ks = 0; ks < KSTEPS; ++ks)
+#pragma unroll
+                                    for (int mt = 0; mt < MT; ++mt)
+                                        umma_f16(d_base + mt * n_tile, a_c + (uint32_t)((dy * HW + dx) * kRow16 + mt * kMtStep + 2 * ks),
+                                                 b_c + (uint32_t)(dx * KS + dy) * bstep + 2 * ks, idesc, (dx | dy | ks) ? 1u : fresh);
+                    }
+                    __syncwarp();
+                    continue;
+                }
+#pragma unroll
+                for (int dx = 0; dx < KS; ++dx) {
+                    const int slot = p.b_resident ? set0 + cc * KS + dx : bs;
+                    if (!p.b_resident) mbar_wait(b_full + 8u * bs, bph);
+                    else if (seen_layer != l) mbar_wait(b_full + 8u * slot, (uint32_t)((l / p.b_sets) & 1));      // first tile of this layer for this warp
+                    tc_fence_after();
+                    const uint64_t b_s = db0 + ((b_base + slot * b_slot_bytes) >> 4);
+                    const uint32_t fresh = (cc == 0 && dx == 0) ? 0u : 1u;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int dy = 0; dy < KS; ++dy) {
+                            const uint64_t bd = b_s + (uint32_t)dy * bstep;
+#pragma unroll
+                            for (int ks = 0; ks < KSTEPS; ++ks)
+#pragma unroll
+                                for (int mt = 0; mt < MT; ++mt)
+                                    umma_f16(d_base + mt * n_tile, a_c + (uint32_t)((dy * HW + dx) * kRow16 + mt * kMtStep + 2 * ks),
+                                             bd + 2 * ks, idesc, (dy | ks) ? 1u : fresh);
+                        }
+                        if (!p.b_resident || last_of_layer) umma_commit(b_empty + 8u * slot);
+                    }
+                    __syncwarp();
+                    if (!p.b_resident && ++bs == p.b_slots) { bs = 0; bph ^= 1u; }
+                }
+            }
+            seen_layer = l;
+            if (elect_one()) {
+                umma_commit(a_empty + 8u * sa);
+                umma_commit(acc_full + 8u * ab);
+            }
+            __syncwarp();
+        }
+      }
+    } else {
+        // ===== epilogue teams: tile s by team s % teams =====
+        const int team = (warp - 4) >> 2;
+        const int grp = warp & 3;
+        const int r = grp * 32 + lane;
+        const bool res_ring = p.res_smem != 0;
+        const uint32_t t_lane0 = tmem_base + ((uint32_t)(grp * 32) << 16);
+        const int teams = p.teams;
+        bool row_ok[2];
+        int row_n[2], row_w;
+        uint32_t row_off[2];
+        uint32_t rs_off[2], rs_xor[2];
+        row_w = r & 7;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int g = mt * 16 + (r >> 3);
+            const int nn = g / p.rs, hh = g - nn * p.rs;
+            row_ok[mt] = mt < MT && nn < p.tn && hh < p.th;
+            row_n[mt] = nn;
+            row_off[mt] = (uint32_t)((((size_t)nn * p.Ho + hh) * p.Wo + row_w) * p.Cout);
+            const uint32_t rrow = row_ok[mt] ? (uint32_t)((nn * p.th + hh) * 8 + row_w) : 0u;
+            rs_off[mt] = rrow * p.r_row_bytes;
+            rs_xor[mt] = p.r_row_bytes == 128 ? (rrow & 7u) : ((rrow >> 1) & 3u);
+        }
+        auto res_lds = [&](uint32_t rst, int mt, int c0, uint4& q0, uint4& q1) {
+            const uint32_t rso = mt ? rs_off[1] : rs_off[0], rsx = mt ? rs_xor[1] : rs_xor[0];
+            const uint32_t box = rst + (uint32_t)(c0 >> 6) * p.r_chunk_bytes + rso;
+            const uint32_t ci = (uint32_t)(c0 & 63) >> 3;
+            const uint32_t a0 = box + (((ci) ^ rsx) << 4), a1 = box + (((ci + 1) ^ rsx) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "r"(a0));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "r"(a1));
+        };
+        pdl_wait();
+        const int groups = (MT * p.n_tile + 31) >> 5;
+        // A finished tile is published -- fence for the async proxy, +1 on its shared-memory counter, and for tiles another
+        // CTA reads a device-scope fence and +1 on the global flag -- just BEFORE the stores of this team's next tile (its own
+        // stores were issued a tile period earlier and have been acknowledged by then, so the fences do not wait for them), or
+        // at once when the team would otherwise sit waiting for its next accumulator.
+        unsigned* pend_g = nullptr;
+        int pend_i = -1;
+        auto publish = [&]() {
+            if (!(p.dbg_flags & 2)) asm volatile("fence.proxy.async;" ::: "memory");
+            if (pend_g && !(p.dbg_flags & 1)) __threadfence(); else __threadfence_block();
+            __syncwarp();
+            if (lane == 0) {
+                if (pend_g) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(pend_g) : "memory");
+                atomicAdd(&s_done[pend_i], 1u);
+            }
+            pend_g = nullptr; pend_i = -1;
+        };
+        for (int s = team; team < teams && s < total; s += teams) {
+            const int l = s / T, q = s - l * T;
+            const ChainTile ct = s_tile[q];
+            const ChainLayer li = s_layer[l];
+            const bool valid0 = row_ok[0] && (int)ct.n0 + row_n[0] < p.P && (int)ct.tw * 8 + row_w < p.Wo;
+            const bool valid1 = row_ok[1] && (int)ct.n0 + row_n[1] < p.P && (int)ct.tw * 8 + row_w < p.Wo;
+            __half* const out0 = li.out + (size_t)(ct.origin + row_off[0]);
+            __half* const out1 = li.out + (size_t)(ct.origin + row_off[1]);
+            const bool has_res = li.has_res != 0, relu = li.relu != 0;
+            const float* bias_l = s_bias + l * p.n_tile;
+            const int abuf = s % p.acc_bufs, k = s / p.acc_bufs;
+            const int sr = s % p.a_stages, lap_r = s / p.a_stages;
+            const uint32_t t_lane = t_lane0 + abuf * acc_stride;
+            const uint32_t rst = r_base + sr * r_tile_bytes;
+            if (li.tl && q == 0 && grp == 0 && lane == 0) atomicMin(li.tl, globaltimer_ns());
+            if (hdr.trace && q == 0 && grp == 0 && lane == 0) hdr.trace[((size_t)blockIdx.x * L + l) * 2] = globaltimer_ns();
+            if (pend_i >= 0) {
+                // next accumulator not there yet: nothing better to do than to publish now
+                uint32_t ready;
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p;\n"
+                    "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                    "selp.u32 %0, 1, 0, p;\n"
+                    "}\n" : "=r"(ready) : "r"(acc_full + 8u * abuf), "r"((uint32_t)(k & 1)) : "memory");
+                if (!__all_sync(0xffffffffu, ready != 0)) publish();
+            }
+            if (res_ring) mbar_wait(res_full + 8u * sr, (uint32_t)(lap_r & 1));
+            mbar_wait(acc_full + 8u * abuf, (uint32_t)(k & 1));
+            tc_fence_after();
+            for (int g = 0; g < groups; ++g) {
+                const int col = g << 5;
+                const int mt = MT == 1 ? 0 : (col >= p.n_tile ? 1 : 0);
+                const int c0 = col - mt * p.n_tile;
+                const bool two = c0 + 32 <= p.n_tile;
+                uint32_t ra[16], rb[16];
+                tmem_ld16(t_lane + (uint32_t)col, ra);
+                if (two) tmem_ld16(t_lane + (uint32_t)(col + 16), rb);
+                tmem_ld_wait();
+                if (g == groups - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty + 8u * abuf) : "memory");
+                }
+                const bool ok = mt ? valid1 : valid0;
+                __half* const o = mt ? out1 : out0;
+                uint4 qv[4] = {};
+                if (has_res) {
+                    res_lds(rst, mt, c0, qv[0], qv[1]);
+                    if (two) res_lds(rst, mt, c0 + 16, qv[2], qv[3]);
+                }
+                if (pend_i >= 0) publish();          // (before this tile's first store)
+                if (ok) {
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        if (hf == 1 && !two) break;
+                        const uint32_t* rr = hf ? rb : ra;
+                        const int cc0 = c0 + 16 * hf;
+                        float x[16];
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias_l + cc0 + 4 * q4);
+                            x[4 * q4] = __uint_as_float(rr[4 * q4]) + b4.x; x[4 * q4 + 1] = __uint_as_float(rr[4 * q4 + 1]) + b4.y;
+                            x[4 * q4 + 2] = __uint_as_float(rr[4 * q4 + 2]) + b4.z; x[4 * q4 + 3] = __uint_as_float(rr[4 * q4 + 3]) + b4.w;
+                        }
+                        if (has_res) {
+                            const __half2* h0p = reinterpret_cast<const __half2*>(&qv[2 * hf]);
+                            const __half2* h1p = reinterpret_cast<const __half2*>(&qv[2 * hf + 1]);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float2 f0 = __half22float2(h0p[u]), f1 = __half22float2(h1p[u]);
+                                x[2 * u] += f0.x; x[2 * u + 1] += f0.y;
+                                x[8 + 2 * u] += f1.x; x[8 + 2 * u + 1] += f1.y;
+                            }
+                        }
+                        if (relu) {
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) x[u] = fmaxf(x[u], 0.f);
+                        }
+                        __align__(16) __half2 pk[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) pk[u] = __floats2half2_rn(x[2 * u], x[2 * u + 1]);
+                        *reinterpret_cast<uint4*>(o + cc0) = *reinterpret_cast<const uint4*>(&pk[0]);
+                        *reinterpret_cast<uint4*>(o + cc0 + 8) = *reinterpret_cast<const uint4*>(&pk[4]);
+                    }
+                }
+            }
+            if (res_ring) {
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(res_empty + 8u * sr) : "memory");
+            }
+            // this warp's rows are stored; the fourth arrival completes the tile
+            if (l + 1 < L) {
+                pend_i = (int)ct.tile - t0;
+                pend_g = ct.outer ? hdr.flags + (size_t)l * p.n_tiles + ct.tile : nullptr;
+            }
+            if (li.tl && q == T - 1 && grp == 0 && lane == 0) atomicMax(li.tl + 1, globaltimer_ns());
+            if (hdr.trace && q == T - 1 && grp == 0 && lane == 0) hdr.trace[((size_t)blockIdx.x * L + l) * 2 + 1] = globaltimer_ns();
+        }
+        if (pend_i >= 0) publish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+    if (threadIdx.x == 0) {
+        // last CTA out closes the launch: the next launch's tiles then show 4 more arrivals
+        __threadfence();
+        const unsigned left = atomicAdd(hdr.state + 1, 1u);
+        if (left == gridDim.x - 1) {
+            hdr.state[1] = 0u;
+            __threadfence();
+            atomicAdd(hdr.state, 1u);
+        }
+    }
+}
+
 int halo_mode_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("HBP_CONV_HALO"); v = e ? atoi(e) : 1; }
@@ -1506,6 +2046,10 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
         HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<4, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_chain_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_chain_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_chain_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
+        HBP_CUDA(cudaFuncSetAttribute(conv_umma_chain_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
         ctx->attr_flags |= ATTR_UMMA;
     }
     if (!for_group && (op.k == 3 || (op.k == 1 && env_int("HBP_HALO_1X1", 1))) && op.stride == 1 && op.up == 1 && halo_mode_enabled()) {
@@ -1812,5 +2356,188 @@ int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, 
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return hbp_cuda_fail(e, "conv_umma_kernel", __FILE__, __LINE__);
+    return HBP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// chain launch (conv_umma_chain_kernel): host side
+// ---------------------------------------------------------------------------
+struct UmmaChain {
+    ChainEntry* d_table = nullptr;
+    unsigned* d_flags = nullptr;         // [n_layers][n_tiles] + 2 words of launch state
+    std::vector<ChainEntry> h;
+    ConvParams prm;
+    ChainHeader hdr;
+    size_t smem = 0;
+    int grid = 0, ksteps = 0;
+    int P = -1;
+    int unsupported = 0;                 // the members run as individual launches
+    const void* tl = nullptr;
+};
+
+void umma_chain_destroy(UmmaChain* c) {
+    if (!c) return;
+    if (c->d_table) cudaFree(c->d_table);
+    if (c->d_flags) cudaFree(c->d_flags);
+    delete c;
+}
+
+static int encode_act_map(EncodeTiledFn enc, CUtensorMap* tm, const HrnetModel& m, const HTensor& t, int capP, int c_box, int w_box,
+                          int h_box, int n_box, uint32_t row_bytes, const char* what) {
+    cuuint64_t gdim[4] = {(cuuint64_t)t.c, (cuuint64_t)t.w, (cuuint64_t)t.h, (cuuint64_t)capP};
+    cuuint64_t gstr[3] = {(cuuint64_t)t.c * 2, (cuuint64_t)t.w * t.c * 2, (cuuint64_t)t.h * t.w * t.c * 2};
+    cuuint32_t box[4] = {(cuuint32_t)c_box, (cuuint32_t)w_box, (cuuint32_t)h_box, (cuuint32_t)n_box};
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, m.bufs[t.buf], gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { hbp_set_error("cuTensorMapEncodeTiled(%s) failed (%d)", what, (int)r); return HBP_ERR_CUDA; }
+    return HBP_OK;
+}
+
+// returns HBP_OK after launching, 1 when the chain cannot run as one kernel (the caller issues the members one by one)
+int umma_chain_launch(hbp_ctx* ctx, HrnetModel& m, int chain_index, int P, cudaStream_t st) {
+    static const int enabled = env_int("HBP_CHAIN", 0);     // measured slower than the per-conv launches at batch 64 (profiles/r02_chain_kernel.md): off by default
+    const HOp& cop = m.ops[chain_index];
+    const int L = (int)cop.members.size();
+    if (!enabled || L < 2 || L > kMaxChain) return 1;
+    if ((int)m.chains.size() < (int)m.ops.size()) m.chains.resize(m.ops.size(), nullptr);
+    UmmaChain*& c = m.chains[chain_index];
+    if (!c) c = new UmmaChain();
+    if (c->unsupported) return 1;
+    if (c->P != P || c->tl != (const void*)m.d_timeline) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        if (cs != cudaStreamCaptureStatusNone) { hbp_set_error("chain table rebuilt inside a capture"); return HBP_ERR_STATE; }
+        // geometry from a member WITH a residual (its ring stage holds halo + residual tile): the most constrained plan
+        int with_res = -1;
+        for (int k = 0; k < L; ++k) if (m.ops[cop.members[k]].res >= 0) { with_res = k; break; }
+        const HOp& op0 = m.ops[cop.members[with_res >= 0 ? with_res : 0]];
+        for (int k = 0; k < L; ++k) {
+            const HOp& o = m.ops[cop.members[k]];
+            const HTensor &ti = m.tensors[o.in], &t0 = m.tensors[op0.in];
+            if (o.k != 3 || o.stride != 1 || o.up != 1 || o.cin != op0.cin || o.cout != op0.cout || o.cin != o.cout || ti.h != t0.h || ti.w != t0.w ||
+                !umma_supported(m, o)) { c->unsupported = 1; return 1; }
+        }
+        UmmaPlan pl;
+        memset(&pl.prm, 0, sizeof(pl.prm));
+        bool ok = false;
+        int stt = plan_halo(ctx, m, op0, m.cap_P, &pl, &ok);
+        if (stt) return stt;
+        ConvParams& p = pl.prm;
+        if (!ok || pl.n_splits != 1 || (with_res >= 0 && !p.res_smem) || p.bias_mma || p.res_mma) { c->unsupported = 1; return 1; }
+        const int tiles_n = (P + p.tn - 1) / p.tn;
+        const int n_tiles = tiles_n * p.tiles_h * p.tiles_w;
+        int grid = std::min(pl.sm_budget, n_tiles);
+        if (grid < 1) grid = 1;
+        if (n_tiles / grid < 4) p.issuers = 1;             // both issuers need a last tile in every layer
+        {
+            const HTensor& to = m.tensors[op0.out];
+            if ((n_tiles + grid - 1) / grid > kMaxChainTiles || (size_t)m.cap_P * to.h * to.w * to.c >= (size_t(1) << 32) ||
+                tiles_n > 65535) { c->unsupported = 1; return 1; }
+        }
+        p.P = P; p.n_tiles = n_tiles; p.dbg = nullptr; p.tl = nullptr; p.dbg_flags = env_int("HBP_CHAIN_DBG", 0);
+        c->prm = p;
+        c->grid = grid;
+        c->ksteps = p.chunk / 16;
+        c->smem = pl.smem_bytes + (size_t)(L - 1) * p.n_tile * 4;
+        p.b_sets = 1;
+        if (p.b_resident) {
+            // a second resident weight set (the next layer's, prefetched a whole layer ahead) when it fits
+            const size_t b_all = (size_t)p.b_slots * 3 * p.b_stage_bytes;
+            if (env_int("HBP_CHAIN_BSETS", 2) >= 2 && c->smem + b_all <= 212 * 1024 && 2 * p.b_slots <= kMaxBSlots) {
+                p.b_sets = 2;
+                c->smem += b_all;
+                p.b_slots *= 2;
+            }
+        }
+        c->prm = p;
+        if (c->smem > 212 * 1024) { c->unsupported = 1; return 1; }     // (the kernel's tables take 12 KB of static shared memory)
+        c->h.assign(L, ChainEntry());
+        EncodeTiledFn enc = get_encode();
+        const int hw = kHaloW;
+        std::vector<int> out_tensor(L);
+        for (int k = 0; k < L; ++k) {
+            const HOp& o = m.ops[cop.members[k]];
+            ChainEntry& e = c->h[k];
+            int s1 = encode_act_map(enc, &e.tmA, m, m.tensors[o.in], m.cap_P, p.chunk, hw, p.rs, p.tn, p.row_bytes, "chain A");
+            if (s1) return s1;
+            e.tmR = e.tmA;
+            if (o.res >= 0) {
+                s1 = encode_act_map(enc, &e.tmR, m, m.tensors[o.res], m.cap_P, (int)(p.r_row_bytes / 2), 8, p.th, p.tn, p.r_row_bytes, "chain residual");
+                if (s1) return s1;
+            }
+            UmmaPlan tmp;
+            s1 = encode_weights_map(enc, &tmp, m, o, p.chunk, p.n_tile, p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+            if (s1) return s1;
+            e.tmB = tmp.tmB;
+            e.bias = m.d_bias + o.b_off;
+            e.out = m.bufs[m.tensors[o.out].buf];
+            e.relu = o.relu; e.has_res = o.res >= 0 ? 1 : 0;
+            e.res_layer = -1;
+            for (int j = 0; j < k; ++j) if (o.res >= 0 && out_tensor[j] == o.res) e.res_layer = j;
+            // the input of layer k must be the output of layer k-1 (that is what the flags order)
+            if (k > 0 && o.in != out_tensor[k - 1]) { c->unsupported = 1; return 1; }
+            out_tensor[k] = o.out;
+            e.tl = m.d_timeline ? m.d_timeline + 2 * cop.members[k] : nullptr;
+        }
+        if (!c->d_table) HBP_CUDA(cudaMalloc(&c->d_table, sizeof(ChainEntry) * kMaxChain));
+        if (c->d_flags) { HBP_CUDA(cudaStreamSynchronize(st)); cudaFree(c->d_flags); c->d_flags = nullptr; }
+        const size_t n_flags = (size_t)L * n_tiles + 2;
+        HBP_CUDA(cudaMalloc(&c->d_flags, n_flags * sizeof(unsigned)));
+        HBP_CUDA(cudaMemsetAsync(c->d_flags, 0, n_flags * sizeof(unsigned), st));
+        HBP_CUDA(cudaMemcpyAsync(c->d_table, c->h.data(), sizeof(ChainEntry) * L, cudaMemcpyHostToDevice, st));
+        HBP_CUDA(cudaStreamSynchronize(st));
+        c->hdr.n_layers = L;
+        c->hdr.flags = c->d_flags;
+        c->hdr.state = c->d_flags + (size_t)L * n_tiles;
+        c->hdr.trace = nullptr;
+        if (getenv("HBP_CHAIN_TRACE") && cop.name.find(getenv("HBP_CHAIN_TRACE")) != std::string::npos) {
+            HBP_CUDA(cudaMalloc(&c->hdr.trace, (size_t)grid * L * 2 * sizeof(unsigned long long)));
+            HBP_CUDA(cudaMemset(c->hdr.trace, 0, (size_t)grid * L * 2 * sizeof(unsigned long long)));
+        }
+        c->P = P;
+        c->tl = m.d_timeline;
+        if (getenv("HBP_CONV_TRACE"))
+            fprintf(stderr, "[chain] %s layers=%d tiles=%d grid=%d (%d..%d tiles per CTA) m=%d n_tile=%d a_stages=%d b_slots=%d resident=%d issuers=%d teams=%d smem=%zu\n",
+                    cop.name.c_str(), L, n_tiles, grid, n_tiles / grid, (n_tiles + grid - 1) / grid, p.m_tiles, p.n_tile, p.a_stages, p.b_slots,
+                    p.b_resident, p.issuers, p.teams, c->smem);
+    }
+    static const int pdl = env_int("HBP_PDL", 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)c->grid); cfg.blockDim = dim3(kHaloThreads); cfg.dynamicSmemBytes = c->smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    const int ks = c->ksteps, mt = c->prm.m_tiles;
+    if (ks == 2 && mt == 1) cudaLaunchKernelEx(&cfg, conv_umma_chain_kernel<2, 1>, (const ChainEntry*)c->d_table, c->prm, c->hdr);
+    else if (ks == 2 && mt == 2) cudaLaunchKernelEx(&cfg, conv_umma_chain_kernel<2, 2>, (const ChainEntry*)c->d_table, c->prm, c->hdr);
+    else if (ks == 4 && mt == 1) cudaLaunchKernelEx(&cfg, conv_umma_chain_kernel<4, 1>, (const ChainEntry*)c->d_table, c->prm, c->hdr);
+    else if (ks == 4 && mt == 2) cudaLaunchKernelEx(&cfg, conv_umma_chain_kernel<4, 2>, (const ChainEntry*)c->d_table, c->prm, c->hdr);
+    else { c->unsupported = 1; return 1; }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return hbp_cuda_fail(e, "conv_umma_chain_kernel", __FILE__, __LINE__);
+    if (c->hdr.trace) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        static int dumps = 0;
+        if (cs == cudaStreamCaptureStatusNone && dumps < 4) {
+            // eager launches only: per CTA the start of its first and the end of its last tile of every layer, us from the launch's first tile
+            ++dumps;
+            cudaDeviceSynchronize();
+            std::vector<unsigned long long> h((size_t)c->grid * L * 2);
+            cudaMemcpy(h.data(), c->hdr.trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            unsigned long long t0 = ~0ull;
+            for (int i = 0; i < c->grid; ++i) if (h[(size_t)i * L * 2] && h[(size_t)i * L * 2] < t0) t0 = h[(size_t)i * L * 2];
+            fprintf(stderr, "[chaintrace] %s grid=%d layers=%d: per CTA 'start0 | end of layer 0..%d' (us)\n", cop.name.c_str(), c->grid, L, L - 1);
+            for (int i = 0; i < c->grid; ++i) {
+                fprintf(stderr, "[chaintrace] cta %3d tiles %3d: %7.1f |", i, (int)(((long long)(i + 1) * c->prm.n_tiles) / c->grid - ((long long)i * c->prm.n_tiles) / c->grid),
+                        (double)(h[(size_t)i * L * 2] - t0) * 1e-3);
+                for (int l = 0; l < L; ++l) fprintf(stderr, " %7.1f", (double)(h[((size_t)i * L + l) * 2 + 1] - t0) * 1e-3);
+                fprintf(stderr, "\n");
+            }
+        }
+    }
     return HBP_OK;
 }

@@ -26,8 +26,9 @@ struct hbp_pipe_slot {
     uint8_t* h_pin = nullptr;    size_t pin_cap = 0;      // pinned mirror of d_misc
     cudaEvent_t ev_h2d = nullptr, ev_crop = nullptr, ev_done = nullptr;
     bool crop_recorded = false, busy = false;
+    bool det_pose = false;                                // the batch in flight came from hbp_det_pose_submit
     int P = 0;
-    size_t par_bytes = 0, res_bytes = 0;
+    size_t par_bytes = 0, res_bytes = 0, hm_bytes = 0;
 };
 
 struct hbp_ctx {
@@ -60,7 +61,8 @@ enum {
     SC_OUT0, SC_OUT1, SC_OUT2, SC_OUT3, SC_OUT4, SC_OUT5, SC_OUT6,  // host-mode output staging
     SC_NMS_CAND, SC_NMS_SORTED, SC_NMS_MASK, SC_NMS_MISC,
     SC_PIPE_CROPS, SC_PIPE_HM, SC_PIPE_MISC, SC_PIPE_FRAMES,
-    SC_PRE_COEF, SC_PRE_TMP                               // PIL-bicubic letterbox: coefficient tables, uint8 intermediate
+    SC_PRE_COEF, SC_PRE_TMP,                              // PIL-bicubic letterbox: coefficient tables, uint8 intermediate
+    SC_PIPE_LB                                            // chained det -> pose pipeline: the detector's letterboxed input tensor
 };
 
 void hbp_set_error(const char* fmt, ...);

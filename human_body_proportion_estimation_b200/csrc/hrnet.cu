@@ -165,19 +165,48 @@ void stage_module(Builder& B, const std::string& pre, std::vector<int>& x, const
             }
         }
     }
+    // The eight convolutions of a branch form an OP_CHAIN: one persistent launch whose CTAs walk the layers with per-tile
+    // dependency flags instead of kernel boundaries (conv_umma_chain_kernel); the executor falls back to the members'
+    // individual launches where the chain kernel does not apply (SIMT engine, the 256-channel per-tap branch).
+    static const bool chained = getenv("HBP_CHAIN") ? atoi(getenv("HBP_CHAIN")) != 0 : false;
     for (int i = 0; i < nb; ++i) {
         B.cur_stream = i;
+        std::vector<int> members;
+        std::vector<int> waits;
+        int join_flag = 0;
+        auto took = [&]() {
+            HOp& o = m.ops.back();
+            o.sm_share = share[i];
+            if (!chained) return;
+            members.push_back((int)m.ops.size() - 1);
+            join_flag |= o.join_before;
+            for (int w : o.wait_ops) if (std::find(waits.begin(), waits.end(), w) == waits.end()) waits.push_back(w);
+            o.join_before = 0; o.wait_ops.clear(); o.grouped = 1;
+        };
         for (int blk = 0; blk < 4; ++blk) {
             const std::string p = pre + S(".branches.%d.%d", i, blk);
             const int t = B.conv(p + ".conv1", x[i], ch[i], 3, 1, 1);
-            m.ops.back().sm_share = share[i];
+            took();
             const int y = B.conv(p + ".conv2", t, ch[i], 3, 1, 1, /*res=*/x[i]);
-            m.ops.back().sm_share = share[i];
+            took();
             B.release(t, true);
             // the module input of blk 0 may have been produced on another stream /
             // is shared: only tensors created inside this loop are stream-local
             B.release(x[i], blk > 0);
             x[i] = y;
+        }
+        if (chained) {
+            HOp g;
+            g.kind = OP_CHAIN;
+            g.name = pre + S(".branches.%d.chain", i);
+            g.members = members;
+            g.stream = i;
+            g.join_before = join_flag;
+            g.wait_ops = waits;
+            g.sm_share = share[i];
+            g.out = x[i];
+            m.ops.push_back(g);
+            B.wrote(x[i], (int)m.ops.size() - 1);
         }
     }
     // fuse: y_i = relu( sum_j f_ij(x_j) ), f_ii = identity.  Terms from higher-resolution
@@ -781,6 +810,8 @@ static void free_batch_state(hbp_ctx* ctx, HrnetModel* m) {
     m->umma.clear();
     for (UmmaGroup* g : m->groups) if (g) umma_group_destroy(g);
     m->groups.clear();
+    for (UmmaChain* c : m->chains) if (c) umma_chain_destroy(c);
+    m->chains.clear();
     for (__half* b : m->bufs) if (b) cudaFree(b);
     m->bufs.clear();
     m->cap_P = 0;
@@ -873,6 +904,7 @@ static int ensure_batch(hbp_ctx* ctx, HrnetModel* m, int P) {
     }
     m->umma.assign(m->ops.size(), nullptr);
     m->groups.assign(m->ops.size(), nullptr);
+    m->chains.assign(m->ops.size(), nullptr);
     return HBP_OK;
 }
 
@@ -990,6 +1022,13 @@ static int issue_ops(hbp_ctx* ctx, HrnetModel* m, const __half* crops, int P, vo
             static const int upadd_bpsm = getenv("HBP_UPADD_BPSM") ? atoi(getenv("HBP_UPADD_BPSM")) : 8;      // blocks per SM over all problems
             const unsigned per_problem = (unsigned)std::max<size_t>(1, (size_t)ctx->sm_count * upadd_bpsm / op.members.size());
             upsample_add_group_kernel<<<dim3(std::min(max_blocks, per_problem), (unsigned)op.members.size()), 256, 0, st>>>(g, P);
+        } else if (op.kind == OP_CHAIN) {
+            int s = m->engine == 1 ? umma_chain_launch(ctx, *m, (int)i, P, st) : 1;
+            if (s < 0) return s;
+            if (s == 1) {                    // member by member
+                for (int k : op.members) { int s2 = issue_conv((size_t)k, st); if (s2) return s2; launches++; }
+                --launches;
+            }
         } else if (op.kind == OP_GROUP) {
             // grouped launch when every member runs on the tensor engine; member by member otherwise
             bool all = m->engine == 1;
@@ -1251,7 +1290,7 @@ extern "C" int hbp_hrnet_describe(int width, int in_h, int in_w, char* buf, size
     std::string s;
     char line[256];
     for (const HOp& op : m.ops) {
-        if (op.kind == OP_UPADD || op.kind == OP_GROUP || op.kind == OP_UPADD_GROUP) continue;            // no parameters
+        if (op.kind == OP_UPADD || op.kind == OP_GROUP || op.kind == OP_UPADD_GROUP || op.kind == OP_CHAIN) continue;            // no parameters
         int ho = 0, wo = 0;
         if (op.kind == OP_STEM1) { ho = m.in_h / 2; wo = m.in_w / 2; }
         else { ho = m.tensors[op.in].h / op.stride; wo = m.tensors[op.in].w / op.stride; }

@@ -15,7 +15,8 @@ struct HTensor {
 
 enum HOpKind { OP_STEM1 = 0, OP_CONV = 1, OP_HEAD = 2, OP_UPADD = 3,
                OP_GROUP = 4,        // one launch that runs `members` (independent OP_CONV ops of one fuse level)
-               OP_UPADD_GROUP = 5   // one launch that runs `members` (the OP_UPADD ops of one fuse stage)
+               OP_UPADD_GROUP = 5,  // one launch that runs `members` (the OP_UPADD ops of one fuse stage)
+               OP_CHAIN = 6         // one persistent launch that runs `members` IN ORDER: the 3x3 convs of one branch of a stage module
 };
 
 // out = act( conv_k,s(in) + bias [+ residual] ), optionally replicated `up` x `up`
@@ -43,6 +44,7 @@ struct HOp {
 
 struct UmmaPlan;                // conv_umma.cu: per-op tensor maps + tile shape (per batch size)
 struct UmmaGroup;               // conv_umma.cu: device table of the member plans of one OP_GROUP launch
+struct UmmaChain;               // conv_umma.cu: device table + dependency flags of one OP_CHAIN launch
 
 struct HrnetModel {
     int width = 32, in_h = 256, in_w = 192;
@@ -60,6 +62,7 @@ struct HrnetModel {
     std::vector<__half*> bufs;
     std::vector<UmmaPlan*> umma;                // one per op (nullptr = SIMT)
     std::vector<UmmaGroup*> groups;             // one per op (OP_GROUP ops only)
+    std::vector<UmmaChain*> chains;             // one per op (OP_CHAIN ops only)
     cudaGraphExec_t graph_exec = nullptr;
     int graph_P = 0, graph_dtype = -1, graph_engine = -1;
     const void* graph_in = nullptr;
@@ -83,3 +86,7 @@ int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* plan, int P
 // one launch for all member convs of the OP_GROUP op `group_index` (plans in m.umma, created with for_group)
 int umma_group_launch(hbp_ctx* ctx, HrnetModel& m, int group_index, int P, cudaStream_t st);
 void umma_group_destroy(UmmaGroup* g);
+// one persistent launch for the member convs of the OP_CHAIN op `chain_index`, in order; returns 1 (nothing launched)
+// when the members have to run as individual launches
+int umma_chain_launch(hbp_ctx* ctx, HrnetModel& m, int chain_index, int P, cudaStream_t st);
+void umma_chain_destroy(UmmaChain* c);

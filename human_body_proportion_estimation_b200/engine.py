@@ -255,7 +255,9 @@ class Engine:
 
     # ---- K6 ----------------------------------------------------------------
     def decode_proportions(self, heatmaps, boxes_yxyx_px=None, height_cm=None,
-                           joint_thr=KEYPOINT_THRES_LIST, quarter_offset=False):
+                           joint_thr=KEYPOINT_THRES_LIST, quarter_offset=False, mats=None, crop_hw=None):
+        """mats (P,2,3) + crop_hw=(crop_h, crop_w): map the keypoints back through the crops' own dst->src matrices
+        (general inverse affine) instead of the reference's box formula."""
         hm = np.ascontiguousarray(heatmaps)
         if hm.dtype not in (np.float32, np.float16):
             hm = hm.astype(np.float32)
@@ -270,6 +272,13 @@ class Engine:
             out.update(kpts_img=np.zeros((P, J, 2), np.float32), ignored=np.zeros((P,), np.uint32))
             if J == 17:
                 out.update(lengths_cm=np.zeros((P, 11), np.float32), torso_cm=np.zeros((P,), np.float64))
+        if mats is not None:
+            M = _c(mats, np.float64).reshape(P, 6)
+            check(self._lib.hbp_decode_proportions_affine(
+                self._ctx, ptr(hm), _NP2HBP[hm.dtype], P, J, Hh, Wh, ptr(boxes), ptr(M), int(crop_hw[0]), int(crop_hw[1]),
+                ptr(hcm), ptr(thr), int(quarter_offset), ptr(out["kpts_hm"]), ptr(out.get("kpts_img")), ptr(out["scores"]),
+                ptr(out["argmax"]), ptr(out.get("ignored")), ptr(out.get("lengths_cm")), ptr(out.get("torso_cm")), HOST))
+            return out
         check(self._lib.hbp_decode_proportions(
             self._ctx, ptr(hm), _NP2HBP[hm.dtype], P, J, Hh, Wh, ptr(boxes), ptr(hcm), ptr(thr),
             int(quarter_offset), ptr(out["kpts_hm"]), ptr(out.get("kpts_img")), ptr(out["scores"]),
@@ -343,6 +352,88 @@ class Engine:
                    torso_cm=np.zeros((P,), np.float64))
         check(self._lib.hbp_pose_pipeline_collect(self._ctx, ticket, ptr(out["kpts_img"]), ptr(out["scores"]),
                                                   ptr(out["ignored"]), ptr(out["lengths_cm"]), ptr(out["torso_cm"])))
+        return out
+
+
+    # ---- chained det -> pose pipeline (configs[2] / [3]) -------------------------------------------------
+    def _det_pose_params(self, frames, detector, persons_cap, swap_rb, quarter_offset, **kw):
+        prm = _capi.DetPoseParams()
+        prm.n_frames, prm.h, prm.w = frames.shape[0], frames.shape[1], frames.shape[2]
+        prm.detector, prm.persons_cap = detector, int(persons_cap)
+        prm.swap_rb, prm.quarter_offset = int(swap_rb), int(quarter_offset)
+        for k, v in kw.items():
+            setattr(prm, k, v)
+        return prm
+
+    def det_pose_submit_yolo(self, frames, pred, person_height=(175,), persons_cap=32, conf_thres=0.4, iou_thres=0.5,
+                             person_class=0, in_size=(640, 640), resample="bilinear", max_det=300, cand_cap=4096,
+                             joint_thr=KEYPOINT_THRES_LIST, swap_rb=False, quarter_offset=False):
+        """frames (F,h,w,3) u8 RGB + decoded YOLOv5 head pred (F,N,5+nc) f32 -> ticket.  The whole chain letterbox ->
+        NMS(person) -> scale_coords -> crop -> HRNet -> decode runs on the device (hbp_det_pose_submit)."""
+        frames = _c(frames, np.uint8)
+        if frames.ndim == 3:
+            frames = frames[None]
+        pred = _c(pred, np.float32)
+        F_, N, E = pred.shape
+        assert F_ == frames.shape[0]
+        prm = self._det_pose_params(frames, _capi.DET_YOLO, persons_cap, swap_rb, quarter_offset, person_class=int(person_class),
+                                    N=N, nc=E - 5, in_h=int(in_size[1]), in_w=int(in_size[0]),
+                                    letterbox_mode=1 if resample == "bicubic" else 0, max_det=int(max_det),
+                                    cand_cap=int(cand_cap), conf_thres=float(conf_thres), iou_thres=float(iou_thres))
+        return self._det_pose_submit(prm, frames, pred, None, None, person_height, joint_thr)
+
+    def det_pose_submit_edet(self, frames, boxes, scores, classes, person_height=(175,), persons_cap=None, det_threshold=0.70,
+                             max_persons=3, x_expand=None, y_expand=0, person_class=1, joint_thr=KEYPOINT_THRES_LIST,
+                             swap_rb=False, quarter_offset=False):
+        """frames (F,h,w,3) u8 as the model sees them + EfficientDet outputs boxes (F,K,4) yxyx px, scores (F,K),
+        classes (F,K) -> ticket.  x_expand defaults to h // 17 like the reference (person_det_pose_edet4_trtserver.py:116)."""
+        frames = _c(frames, np.uint8)
+        if frames.ndim == 3:
+            frames = frames[None]
+        boxes, scores, classes = _c(boxes, np.float32), _c(scores, np.float32), _c(classes, np.float32)
+        if boxes.ndim == 2:
+            boxes, scores, classes = boxes[None], scores[None], classes[None]
+        F_, K = scores.shape
+        assert F_ == frames.shape[0]
+        if x_expand is None:
+            x_expand = frames.shape[1] // 17
+        if persons_cap is None:
+            persons_cap = F_ * max_persons
+        prm = self._det_pose_params(frames, _capi.DET_EDET, persons_cap, swap_rb, quarter_offset, person_class=int(person_class),
+                                    K=K, max_persons=int(max_persons), det_thres=float(det_threshold),
+                                    x_expand=float(x_expand), y_expand=float(y_expand))
+        return self._det_pose_submit(prm, frames, boxes, scores, classes, person_height, joint_thr)
+
+    def _det_pose_submit(self, prm, frames, d0, d1, d2, person_height, joint_thr):
+        hts = _c(np.atleast_1d(np.asarray(person_height, np.float64)), np.float64)
+        thr = _c(joint_thr, np.float32)
+        ticket = C.c_int(-1)
+        check(self._lib.hbp_det_pose_submit(self._ctx, C.byref(prm), ptr(frames), ptr(d0), ptr(d1), ptr(d2), ptr(hts), hts.size,
+                                            ptr(thr), C.byref(ticket)))
+        if not hasattr(self, "_inflight"):
+            self._inflight = {}
+        self._inflight[ticket.value] = ((frames, d0, d1, d2), int(prm.persons_cap))     # buffers stay alive until collect
+        return ticket.value
+
+    def det_pose_collect(self, ticket, return_heatmaps=False):
+        """-> dict(n, status, frame_idx (n), boxes_yxyx_px (n,4), kpts_img (n,17,2), scores (n,17), ignored (n),
+        lengths_cm (n,11), torso_cm (n) [, heatmaps (n,17,Hh,Wh) f16])"""
+        _, cap = self._inflight.pop(ticket)
+        out = dict(frame_idx=np.zeros(cap, np.int32), boxes_yxyx_px=np.zeros((cap, 4), np.float32),
+                   kpts_img=np.zeros((cap, 17, 2), np.float32), scores=np.zeros((cap, 17), np.float32),
+                   ignored=np.zeros(cap, np.uint32), lengths_cm=np.zeros((cap, 11), np.float32), torso_cm=np.zeros(cap, np.float64))
+        n, status = C.c_int(0), C.c_int(0)
+        hm = None
+        if return_heatmaps:
+            _, ih, iw = self.hrnet
+            hm = np.zeros((cap, 17, ih // 4, iw // 4), np.float16)
+        check(self._lib.hbp_det_pose_collect(self._ctx, ticket, C.byref(n), C.byref(status), ptr(out["frame_idx"]),
+                                             ptr(out["boxes_yxyx_px"]), ptr(out["kpts_img"]), ptr(out["scores"]), ptr(out["ignored"]),
+                                             ptr(out["lengths_cm"]), ptr(out["torso_cm"]), ptr(hm)))
+        out = {k: v[:n.value] for k, v in out.items()}
+        out["n"], out["status"] = n.value, status.value
+        if hm is not None:
+            out["heatmaps"] = hm[:n.value]
         return out
 
 

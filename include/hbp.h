@@ -264,6 +264,60 @@ HBP_API int hbp_pose_pipeline_submit(hbp_ctx* ctx, const hbp_pipeline_params* pr
 HBP_API int hbp_pose_pipeline_collect(hbp_ctx* ctx, int ticket, float* kpts_img, float* scores,
                               uint32_t* ignored, float* lengths_cm, double* torso_cm);
 
+/* ---- chained det -> pose pipeline (BASELINE configs[2], [3]) ---------------- *
+ * Frames plus the detector's output tensors in, per-person results out, no host round trip between the stages:
+ *   HBP_DET_YOLO: letterbox (hble/obj_det_yolov5_onnx.py:27-36) -> non_max_suppression on the decoded head
+ *     (hble/modules/onnx_utils.py:125-222; det0 = (F,N,5+nc) f32, det1 = det2 = NULL; person_class >= 0 filters that
+ *     class, < 0 keeps all) -> scale_coords (:252-266) -> int() box, cv2.resize-style crop
+ *     (hble/modules/pose_estimator.py:29-45) -> HRNet -> decode + proportions.  Persons in score order per frame.
+ *   HBP_DET_EDET: EfficientDet outputs det0 = boxes (F,K,4) yxyx px, det1 = scores (F,K), det2 = classes (F,K) ->
+ *     person filter / expansion (models/conv.py:22-57) -> tf.image.crop_and_resize crop (:59-70) -> HRNet -> decode
+ *     + proportions (hble/person_det_pose_edet4_trtserver.py:145-171).  Persons in detector order per frame.
+ * The detector backbones are not part of the reference tree (README.md:13-26): their outputs are inputs here.
+ * heights: person i of a frame gets heights[min(i, n_heights-1)] (hble/person_det_pose_edet4_trtserver.py:166-168).
+ * Every call computes persons_cap person slots (one CUDA graph whatever a frame holds); *n_persons <= persons_cap
+ * come back, in frame order.  status bit 0: an image had more NMS candidates than cand_cap; bit 1: more persons than
+ * persons_cap (the surplus was dropped).  Same two-slot submit / collect protocol as hbp_pose_pipeline_submit. */
+typedef enum { HBP_DET_YOLO = 0, HBP_DET_EDET = 1 } hbp_detector;
+typedef struct {
+    int n_frames, h, w;            /* frames (n_frames,h,w,3) u8 */
+    int detector;                  /* hbp_detector */
+    int persons_cap;
+    int swap_rb, quarter_offset;
+    int person_class;              /* YOLO: class id kept (reference callers: 0), EDET: class value kept (1) */
+    /* YOLO */
+    int N, nc, in_h, in_w;         /* head rows, classes, detector input size (640x640) */
+    int letterbox_mode;            /* 0 = cv2-bilinear letterbox, 1 = the reference's PIL bicubic */
+    int max_det, cand_cap;         /* kept boxes per frame (reference 300), NMS candidate capacity (multiple of 32) */
+    float conf_thres;
+    double iou_thres;
+    /* EDET */
+    int K, max_persons;            /* detector rows per frame (100), persons kept per frame (reference 3) */
+    float det_thres, x_expand, y_expand;
+    int mem;                       /* where frames / det0 / det1 / det2 live: HBP_HOST (copied in, the default) or HBP_DEVICE
+                                      (used in place: the device-resident form bench.py times as `value`) */
+} hbp_det_pose_params;
+HBP_API int hbp_det_pose_submit(hbp_ctx* ctx, const hbp_det_pose_params* prm, const uint8_t* frames,
+                        const float* det0, const float* det1, const float* det2,
+                        const double* heights, int n_heights, const float* joint_thr, int* ticket);
+/* any output may be NULL; arrays are sized for persons_cap rows, the first *n_persons are written.
+ * heatmaps_f16: optional (persons_cap,17,Hh,Wh) fp16, valid until the next submit on this context. */
+HBP_API int hbp_det_pose_collect(hbp_ctx* ctx, int ticket, int* n_persons, int* status, int* frame_idx,
+                         float* boxes_yxyx_px, float* kpts_img, float* scores, uint32_t* ignored,
+                         float* lengths_cm, double* torso_cm, void* heatmaps_f16);
+
+/* ---- K6 with a general inverse affine (north_star item 5) -------------------- *
+ * hbp_decode_proportions with one more input: M (P,6) double, the crop's dst->src matrices (what hbp_crop_warp
+ * sampled with).  Keypoints are mapped back through them -- (u,v) = (x*crop_w/Wh, y*crop_h/Hh), image = M*(u,v,1) in
+ * double, rounded once to float32 -- instead of the reference's box formula, so rotated / aspect-padded crops map
+ * back exactly; boxes still provide pixel_to_cm = height_cm / (y2 - y1). */
+HBP_API int hbp_decode_proportions_affine(hbp_ctx* ctx, const void* heatmaps, int dtype, int P, int J,
+                           int Hh, int Wh, const float* boxes_yxyx_px, const double* M, int crop_h, int crop_w,
+                           const double* height_cm, const float* joint_thr,
+                           int quarter_offset, float* kpts_hm, float* kpts_img,
+                           float* scores, int32_t* argmax_idx, uint32_t* ignored,
+                           float* lengths_cm, double* torso_cm, int mem);
+
 #ifdef __cplusplus
 }
 #endif
