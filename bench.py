@@ -2,26 +2,31 @@
 """Benchmark of the top-down pose hot path (BASELINE.json metric: person crops/sec
 through det -> crop -> HRNet -> decode).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): BASELINE.json configs[1] -- HRNet-W32 256x192 fp16 on 64
-synthetic person crops from one 1080p frame per step and per GPU.  One step =
-crop (K4) -> HRNet (K5, 293 launches in one CUDA graph) -> decode + proportions (K6).
-The detector-head stages (K1 letterbox, K2/K3 NMS) are timed beside it on the
-configs[2] shapes and reported under "stages_ms" (they do not gate the crops).
+One step = ONE call of the chained pipeline (hbp_det_pose_submit / _collect): frames + detector-head tensors ->
+letterbox (K1) -> person filter + NMS (K2/K3) -> scale_coords + per-person crop parameters -> crop (K4) ->
+HRNet (K5, one CUDA graph) -> decode + proportions (K6), no host round trip between the stages.  The detector
+BACKBONES are not part of the reference tree (Google-Drive artifacts), so their output tensors are synthetic inputs.
 
-  value     crops/s with the frame and parameters resident in HBM, device-timed with
-            CUDA events on the library's stream, L2 flushed between steps
-  e2e       crops/s through the public API (Engine.pose_pipeline) with HOST buffers:
-            pinned-host frame -> H2D -> crop -> HRNet -> decode -> D2H of the results
-  roofline  HRNet conv stack: algorithmic FLOPs (2 x MACs of the 293 convs x 64 crops)
-            / CUDA-event time of the HRNet stage inside the timed steps, against the
-            measured sustained bf16 peak of MEASURED_PEAKS.json
+Workloads (config.workload):
+  --config 1 (default, the headline)  BASELINE configs[1]: HRNet-W32 256x192 fp16, 64 person crops from one 1080p frame
+              per step and GPU; the 64 persons come out of the YOLO head stage (synthetic decoded head whose NMS keeps 64)
+  --config 2  BASELINE configs[2]: YOLOv5s 640x640 head (30 planted persons + distractors) -> HRNet-W32, per frame
+  --config 3  BASELINE configs[3]: EfficientDet outputs -> HRNet-W48 384x288, 16 frames x 16 persons per step
+
+  value     crops/s with frames and head tensors resident in HBM (params.mem = HBP_DEVICE), device-timed with CUDA
+            events on the library's stream, L2 flushed between steps
+  e2e       crops/s through the public API (Engine.det_pose_submit_* / det_pose_collect) with HOST buffers: pinned frame
+            and head tensors -> H2D -> chain -> D2H of the results, two batches in flight
+  roofline  HRNet conv stack: algorithmic FLOPs (2 x MACs of the 293 convs x person slots computed) / CUDA-event time
+            of the HRNet stage, against the measured sustained bf16 peak of MEASURED_PEAKS.json
   cpu_baseline / --impl reference
-            the reference's CPU path on the box's host cores: cv2.warpAffine crops,
-            torch fp32 HRNet (stand-in for onnxruntime, which is not installable
-            offline) and the oracle's per-person decode loop, on a bounded sample
+            the reference's CPU path on the box's host cores, from oracle/ only (never loads libhbp_b200.so): PIL
+            letterbox, torchvision NMS via the reference's algorithm restated, cv2.warpAffine crops, torch fp32 HRNet
+            (stand-in for onnxruntime, which is not installable offline), the reference's per-person decode loop
+After the timed regions the e2e results are checked against the oracle on the device's own heatmaps.
 """
 import argparse
 import json
@@ -37,21 +42,34 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CROPS_PER_FRAME = 64
 FRAME_H, FRAME_W = 1080, 1920
-WIDTH, IN_H, IN_W = 32, 256, 192
 METRIC = "person crops/sec (det->crop->HRNet->decode)"
 UNIT = "crops/s"
+HEIGHTS = [175.0]
+
+CONFIGS = {
+    1: dict(name="configs[1]", detector="yolo", width=32, in_h=256, in_w=192, frames=1, persons=64, cap=64,
+            text="configs[1]: HRNet-W32 256x192 fp16, 64 synthetic person crops from one 1080p frame per step per GPU "
+                 "(letterbox -> YOLO-head NMS(person) -> scale_coords -> crop -> HRNet -> decode+proportions)"),
+    2: dict(name="configs[2]", detector="yolo", width=32, in_h=256, in_w=192, frames=1, persons=None, cap=48,
+            text="configs[2]: YOLOv5s 640x640 head (25200x85, 30 planted persons + 300 distractors) + NMS feeding HRNet-W32 "
+                 "256x192 crops, end to end per 1080p frame (48 person slots computed)"),
+    3: dict(name="configs[3]", detector="edet", width=48, in_h=384, in_w=288, frames=16, persons=256, cap=256,
+            text="configs[3]: EfficientDet outputs (100 rows/frame) -> person filter -> HRNet-W48 384x288 -> proportions, "
+                 "batch of 16 1080p frames x 16 persons"),
+}
 
 
-def workload():
-    from human_body_proportion_estimation_b200 import geometry, synth
-    frame = synth.frame_u8(FRAME_H, FRAME_W, seed=synth.SEED_BASE + 2)
-    boxes = synth.person_boxes_yxyx_px(CROPS_PER_FRAME, FRAME_H, FRAME_W, seed=synth.SEED_BASE + 2,
-                                       hmin=150, hmax=900)
-    boxes_n = boxes / np.array([FRAME_H, FRAME_W, FRAME_H, FRAME_W], np.float32)
-    mats = geometry.crop_and_resize_matrices(boxes_n, FRAME_H, FRAME_W, IN_H, IN_W)
-    return frame, boxes, mats
+def synth_inputs(cfg):
+    """(frames (F,h,w,3) u8 RGB, detector tensors tuple) -- numpy only, shared by both arms"""
+    from human_body_proportion_estimation_b200 import synth
+    F = cfg["frames"]
+    frames = np.stack([synth.frame_u8(FRAME_H, FRAME_W, seed=synth.SEED_BASE + 2 + i) for i in range(F)])
+    if cfg["detector"] == "yolo":
+        pred = synth.yolo_head_grid()[0] if cfg["persons"] == 64 else synth.yolo_decoded_head()[0]
+        return frames, (pred,)
+    b, s, c = synth.edet_outputs(F, 16, FRAME_H, FRAME_W)
+    return frames, (b, s, c)
 
 
 def peaks():
@@ -77,10 +95,8 @@ class ClockSampler:
                  "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
-            # nvidia-smi needs a few hundred ms to come up: wait for its first line so that the timed region that
-            # follows is sampled from its start; lines that arrived before `mark()` are dropped
             t0 = time.time()
-            while not self.lines and time.time() - t0 < 3.0:
+            while not self.lines and time.time() - t0 < 3.0:       # first sample before the timed region starts
                 time.sleep(0.01)
         except Exception:
             self.proc = None
@@ -103,7 +119,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        region = self.lines[self.first:] or self.lines[-1:]      # (a region shorter than one period: the sample just before it)
+        region = self.lines[self.first:] or self.lines[-1:]
         for ln in region:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
@@ -120,76 +136,88 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------
-# CPU reference arm / cpu_baseline
+# CPU reference arm / cpu_baseline: oracle/ only, never the library under test
 # --------------------------------------------------------------------------
-def cpu_reference_run(n_crops, steps, warmup, weights=None):
-    """The reference's CPU path on `n_crops` crops of the workload per step.  Returns
-    (crops_per_s, ms_per_step, cores, note)."""
+def cpu_reference_run(cfg, steps, warmup, frames=None, dets=None):
+    """The reference's CPU path on the config's workload, one full batch per step.
+    Returns (crops_per_s, ms_per_step, cores, note)."""
     import torch
-    from human_body_proportion_estimation_b200 import hrnet_arch
+    from oracle import detect as od
     from oracle import geometry as og
+    from oracle import hrnet_table, imgproc
     from oracle.hrnet_fp32 import HRNetFP32
-    try:
-        import cv2
-        have_cv2 = True
-    except Exception:
-        have_cv2 = False
-        from oracle import imgproc
-    frame, boxes, mats = workload()
-    if weights is None:
-        weights = hrnet_arch.random_weights(WIDTH, IN_H, IN_W, seed=0)
-    net = HRNetFP32(weights, WIDTH)
-    # all the host threads the process may use: torchrun exports OMP_NUM_THREADS=1 for every rank, which would time
-    # the reference single-threaded at N > 1
+    import cv2
+    if frames is None:
+        frames, dets = synth_inputs(cfg)
+    if cfg["width"] == 48 and frames.shape[0] > 2:       # bounded sample: 2 of the 16 frames (32 of the 256 W48 crops) per step
+        frames, dets = frames[:2], tuple(d[:2] for d in dets)
+    net = HRNetFP32(hrnet_table.random_weights(cfg["width"], seed=0), cfg["width"])
     try:
         avail = len(os.sched_getaffinity(0))
     except Exception:
         avail = os.cpu_count() or 1
-    if torch.get_num_threads() < avail:
+    if torch.get_num_threads() < avail:      # torchrun exports OMP_NUM_THREADS=1 for every rank
         torch.set_num_threads(avail)
     cores = torch.get_num_threads()
-    if have_cv2:
-        cv2.setNumThreads(cores)
+    cv2.setNumThreads(cores)
+    ih, iw = cfg["in_h"], cfg["in_w"]
+    H, W = frames.shape[1:3]
 
     def step():
-        crops = []
-        for p in range(n_crops):
-            if have_cv2:      # the north-star crop gate: cv2.warpAffine on the u8 frame
-                c = cv2.warpAffine(frame, mats[p], (IN_W, IN_H), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP,
-                                   borderMode=cv2.BORDER_CONSTANT, borderValue=0)
-                c = cv2.cvtColor(c, cv2.COLOR_BGR2RGB)
-                crops.append(np.transpose(c / 255.0, (2, 0, 1)).astype(np.float32))
+        crops, boxes_px, hts = [], [], []
+        for f in range(frames.shape[0]):
+            if cfg["detector"] == "yolo":
+                imgproc.letterbox_pil(frames[f], 640, 640)                       # obj_det_yolov5_onnx.py:27-36 (PIL bicubic)
+                det = od.official_nms(dets[0][f:f + 1], 0.4, 0.5, classes=[0])[0]
+                b = od.scale_coords((640, 640), det[:, :4].copy(), (H, W))
+                for i, bb in enumerate(b):
+                    x1, y1, x2, y2 = (int(v) for v in bb)
+                    M = imgproc.box_resize_matrix((x1, y1, x2, y2), ih, iw)
+                    c = cv2.warpAffine(frames[f], M, (iw, ih), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP,
+                                       borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+                    crops.append(np.transpose(c / 255.0, (2, 0, 1)).astype(np.float32))
+                    boxes_px.append(np.array([y1, x1, y2, x2], np.float32))
+                    hts.append(HEIGHTS[min(i, len(HEIGHTS) - 1)])
             else:
-                crops.append(imgproc.crop_persons(frame, [mats[p]], IN_H, IN_W, True, np.float32)[0])
-        hm = net(np.stack(crops)).numpy()                      # torch fp32, all host threads
-        out = []
-        for p in range(n_crops):                                # reference's per-person python loop
-            out.append(og.person_postprocess(hm[p], boxes[p], 175)["lengths"])
-        return out
+                bn, _ = od.edet_person_filter(dets[0][f], dets[1][f], dets[2][f], 0.70, H // 17, 0, H, W, 16)
+                for i, b in enumerate(bn):
+                    M = imgproc.crop_and_resize_matrix(b, H, W, ih, iw)
+                    c = cv2.warpAffine(frames[f], M, (iw, ih), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP,
+                                       borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+                    crops.append(np.transpose(c / 255.0, (2, 0, 1)).astype(np.float32))
+                    boxes_px.append(b * np.array([H, W, H, W], np.float32))
+                    hts.append(HEIGHTS[min(i, len(HEIGHTS) - 1)])
+        hm = net(np.stack(crops)).numpy()                       # torch fp32, all host threads
+        out = [og.person_postprocess(hm[p], boxes_px[p], hts[p])["lengths"] for p in range(len(crops))]
+        return len(out)
 
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
+    n = 0
     for _ in range(steps):
-        step()
+        n += step()
     dt = time.perf_counter() - t0
-    note = ("%d of the %d crops of one 1080p frame per step: %s crop, torch-fp32 HRNet-W32 (stand-in for "
-            "onnxruntime CPU), oracle decode loop" % (n_crops, CROPS_PER_FRAME,
-                                                      "cv2.warpAffine" if have_cv2 else "numpy cv2-exact"))
-    return n_crops * steps / dt, dt / steps * 1e3, cores, note
+    note = ("one full batch of the workload per step (%d crops): PIL-bicubic letterbox / NMS or EfficientDet person filter "
+            "(oracle restatement of the reference), cv2.warpAffine crops, torch-fp32 HRNet-W%d on %d threads (stand-in for "
+            "onnxruntime CPU), the reference's per-person decode + proportions loop" % (n // max(steps, 1), cfg["width"], cores))
+    return n / dt, dt / steps * 1e3, cores, note
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    n = 8
-    val, ms, cores, note = cpu_reference_run(n, max(1, args.steps), max(0, min(args.warmup, 1)))
+    cfg = CONFIGS[args.config]
+    # bounded: the CPU path needs ~1 s per 64-crop W32 batch; cap the number of timed steps so the run ends in minutes
+    steps = max(1, min(args.steps, 10 if cfg["width"] == 32 else 2))
+    warm = max(1, min(args.warmup, 2 if cfg["width"] == 32 else 1))
+    val, ms, cores, note = cpu_reference_run(cfg, steps, warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": note},
+        "config": config_dict(cfg),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": note + "; %d timed steps" % steps},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(json.dumps(line))
@@ -198,12 +226,11 @@ def run_reference(args, rank):
 def hrnet_traffic():
     """DRAM bytes per HRNet launch from the committed ncu launch list (profiles/*_hrnet_traffic.json, written by
     tools/launch_summary.py): bench.py cannot run ncu on itself."""
-    here = os.path.dirname(os.path.abspath(__file__))
     best = None
     try:
-        for f in sorted(os.listdir(os.path.join(here, "profiles"))):
+        for f in sorted(os.listdir(os.path.join(ROOT, "profiles"))):
             if f.endswith("_hrnet_traffic.json"):
-                best = os.path.join(here, "profiles", f)
+                best = os.path.join(ROOT, "profiles", f)
         if best:
             d = json.load(open(best))
             d["note"] = "dram__bytes_read+write per launch, average over the %d launches of one forward (%s)" % (
@@ -214,18 +241,18 @@ def hrnet_traffic():
     return {}
 
 
-def config_dict():
-    return {"workload": "configs[1]: HRNet-W32 256x192 fp16, 64 synthetic person crops from one 1080p frame "
-                        "per step per GPU (crop -> HRNet -> decode+proportions)",
-            "frame": [FRAME_H, FRAME_W, 3], "crops_per_step_per_gpu": CROPS_PER_FRAME,
-            "hrnet": "W%d %dx%d" % (WIDTH, IN_H, IN_W), "weights": "random-init (seed 0), BN folded",
+def config_dict(cfg):
+    return {"workload": cfg["text"], "frame": [FRAME_H, FRAME_W, 3], "frames_per_step_per_gpu": cfg["frames"],
+            "person_slots_per_step_per_gpu": cfg["cap"],
+            "hrnet": "W%d %dx%d" % (cfg["width"], cfg["in_h"], cfg["in_w"]), "weights": "random-init (seed 0), BN folded",
+            "detector_outputs": "synthetic (the backbones are opaque artifacts outside the reference tree)",
             "l2": "flushed between timed steps (256 MiB write)", "parallelism": "frame-sharded, no collective"}
 
 
 # --------------------------------------------------------------------------
-# memory-bound stages on batched launches (at the config shapes K1/K4/K6 move a
+# memory-bound stages on batched launches (at the config shapes K1/K2/K4/K6 move a
 # few MB per call = microseconds of HBM time, below launch latency; their roofline fraction is
-# measured on launches sized to hundreds of MB, algorithmic bytes / CUDA-event time / measured HBM peak)
+# measured on launches sized to ~1 GB, algorithmic bytes / CUDA-event time / measured HBM peak)
 # --------------------------------------------------------------------------
 def stage_rooflines(eng, hbm_gbs):
     import ctypes as C
@@ -262,29 +289,53 @@ def stage_rooflines(eng, hbm_gbs):
     ms = timed(lambda: check(lib.hbp_preprocess(ctx, C.c_void_p(d_frames), nf, fh, fw, PRE_COPY, fh, fw, 1, 128,
                                                 C.c_void_p(d_copy), U8, NHWC, DEVICE)))
     entry("k1_bgr2rgb_copy_64x4k_u8", 2 * nf * frame.nbytes, ms, "64 frames 2160x3840x3 u8, one launch")
+    # the 6:1 bilinear downscale taps 2 of every 6 source rows; inside a tapped row the taps are 18 bytes apart, below the
+    # 32-byte DRAM sector, so the whole row is fetched: bytes = tapped rows x row bytes + output
+    nh = int(fh * min(640 / fw, 640 / fh))
+    tapped = 2 * nh * fw * 3
     ms = timed(lambda: check(lib.hbp_preprocess(ctx, C.c_void_p(d_frames), nf, fh, fw, PRE_LETTERBOX, 640, 640, 1, 128,
                                                 C.c_void_p(d_lb), F16, NCHW, DEVICE)))
-    entry("k1_letterbox_64x4k_to_640_f16", nf * (frame.nbytes + 3 * 640 * 640 * 2), ms,
-          "64 frames 2160x3840x3 u8 -> 3x640x640 f16, one launch (bytes = whole frame + output)")
+    entry("k1_letterbox_64x4k_to_640_f16", nf * (tapped + 3 * 640 * 640 * 2), ms,
+          "64 frames 2160x3840x3 u8 -> 3x640x640 f16, one launch (bytes = the %d source rows the bilinear taps touch, whole rows, + output)" % (2 * nh))
     ms = timed(lambda: check(lib.hbp_preprocess(ctx, C.c_void_p(d_frames), nf, fh, fw, PRE_LETTERBOX_PIL, 640, 640, 1, 128,
                                                 C.c_void_p(d_lb), F16, NCHW, DEVICE)))
     entry("k1_letterbox_pil_bicubic_64x4k_to_640_f16", nf * (frame.nbytes + 3 * 640 * 640 * 2), ms,
-          "64 frames 2160x3840x3 u8 -> 3x640x640 f16 with PIL's antialiased bicubic (two passes, u8 intermediate), bytes = whole frame + output")
+          "64 frames 2160x3840x3 u8 -> 3x640x640 f16 with PIL's antialiased bicubic (every source pixel is a tap: bytes = whole frame + output)")
     eng.dev_free(d_copy); eng.dev_free(d_lb)
 
     # K4: 4096 crops (64 per frame) from the 64 4K frames -> (4096,3,256,192) f16
     P = 4096
     boxes = synth.person_boxes_yxyx_px(P, fh, fw, seed=synth.SEED_BASE + 6, hmin=300, hmax=1400)
-    mats = geometry.crop_and_resize_matrices(boxes / np.array([fh, fw, fh, fw], np.float32), fh, fw, IN_H, IN_W)
+    mats = geometry.crop_and_resize_matrices(boxes / np.array([fh, fw, fh, fw], np.float32), fh, fw, 256, 192)
     fidx = (np.arange(P) // 64).astype(np.int32)
     d_m = eng.to_device(mats.reshape(P, 6)); d_fi = eng.to_device(fidx)
-    d_cr = eng.dev_alloc(P * 3 * IN_H * IN_W * 2)
+    d_cr = eng.dev_alloc(P * 3 * 256 * 192 * 2)
     ms = timed(lambda: check(lib.hbp_crop_warp(ctx, C.c_void_p(d_frames), nf, fh, fw, C.c_void_p(d_m), C.c_void_p(d_fi),
-                                               P, IN_H, IN_W, 1, C.c_void_p(d_cr), F16, DEVICE)))
+                                               P, 256, 192, 1, C.c_void_p(d_cr), F16, DEVICE)))
     bw = np.clip(boxes[:, 3] - boxes[:, 1], 1, None); bh = np.clip(boxes[:, 2] - boxes[:, 0], 1, None)
-    src = float(np.minimum(bw * bh, 4.0 * IN_H * IN_W).sum()) * 3          # min(box area, 4 taps per output pixel) x 3 B
-    entry("k4_crop_4096x256x192_f16", src + P * 3 * IN_H * IN_W * 2, ms, "4096 crops from 64 4K frames, one launch")
+    src = float(np.minimum(bw * bh, 4.0 * 256 * 192).sum()) * 3          # min(box area, 4 taps per output pixel) x 3 B
+    entry("k4_crop_4096x256x192_f16", src + P * 3 * 256 * 192 * 2, ms, "4096 crops from 64 4K frames, one launch")
     eng.dev_free(d_frames); eng.dev_free(d_m); eng.dev_free(d_fi); eng.dev_free(d_cr)
+
+    # K2: candidate filter on 128 decoded heads (25200 x 85 f32 = 8.568 MB each, 1.1 GB): hbp_yolo_nms with a threshold no
+    # row passes, so that only the filter (+ the empty gather) runs
+    B = 128
+    pred = synth.yolo_decoded_head()[0]
+    d_pred = eng.dev_alloc(B * pred.nbytes)
+    for i in range(B):
+        eng.h2d(d_pred + i * pred.nbytes, pred)
+    d_det = eng.dev_alloc(B * 300 * 6 * 4); d_cnt = eng.dev_alloc(B * 4)
+    d_cls = eng.to_device(np.zeros(1, np.int32))
+    ms = timed(lambda: check(lib.hbp_yolo_filter(ctx, C.c_void_p(d_pred), B, 25200, 80, 0.4, C.c_void_p(d_cls), 1, 4096,
+                                                 C.c_void_p(d_cnt), DEVICE)))
+    cnt = np.zeros(B, np.int32)
+    eng.d2h(cnt, d_cnt); eng.sync()
+    # what the filter has to move: the objectness column (one 32-byte sector of every 340-byte row) and the full rows of the
+    # candidates (obj > conf) -- the reference gathers exactly those rows (onnx_utils.py:133,168)
+    entry("k2_yolo_filter_128x25200x85_f32", B * 25200 * 32 + int(cnt.sum()) * 85 * 4, ms,
+          "128 decoded heads (1.1 GB resident), one filter launch, %d candidates per head: bytes = one sector per row + the candidates' rows" % int(cnt[0]))
+    eng.dev_free(d_cls)
+    eng.dev_free(d_pred); eng.dev_free(d_det); eng.dev_free(d_cnt)
 
     # K6: decode + proportions on 8192 crops of (17,64,48) f16
     P = 8192
@@ -305,16 +356,36 @@ def stage_rooflines(eng, hbm_gbs):
     return out
 
 
+def check_against_oracle(out, heights):
+    """the chain's decode / remap / gate / lengths on ITS OWN heatmaps equal the oracle's per-person loop (checker only,
+    outside every timed region)"""
+    from oracle import geometry as og
+    n = out["n"]
+    for i in range(n):
+        # person index inside its frame decides the height (person_det_pose_edet4_trtserver.py:166-168)
+        j = int((out["frame_idx"][:i] == out["frame_idx"][i]).sum())
+        r = og.person_postprocess(out["heatmaps"][i].astype(np.float32), out["boxes_yxyx_px"][i], heights[min(j, len(heights) - 1)])
+        if not np.array_equal(out["kpts_img"][i], r["xy_img"]):
+            return "keypoints of person %d differ from the oracle" % i
+        if int(out["ignored"][i]) != sum(1 << k for k in r["ignored"]):
+            return "ignored set of person %d differs from the oracle" % i
+        got = out["lengths_cm"][i].astype(np.float64)
+        got[1] = out["torso_cm"][i]
+        if not np.array_equal(got, og.lengths_to_array(r["lengths"])):
+            return "lengths of person %d differ from the oracle" % i
+    return "ok (%d persons: keypoints, ignored sets and 11 lengths bit-exact vs oracle.geometry on the device's heatmaps)" % n
+
+
 # --------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import ctypes as C
-    from human_body_proportion_estimation_b200 import _capi, hrnet_arch, synth
+    from human_body_proportion_estimation_b200 import _capi, hrnet_arch
     from human_body_proportion_estimation_b200.engine import Engine, KEYPOINT_THRES_LIST
-    from human_body_proportion_estimation_b200._capi import DEVICE, F16, F32, NCHW, PRE_LETTERBOX, PRE_LETTERBOX_PIL, check, ptr
-
+    from human_body_proportion_estimation_b200._capi import DEVICE, F16, NCHW, PRE_LETTERBOX, PRE_LETTERBOX_PIL, check, ptr
     from human_body_proportion_estimation_b200 import dist_util
+    cfg = CONFIGS[args.config]
     if world > 1:
         import torch
         torch.cuda.set_device(local_rank)
@@ -322,44 +393,48 @@ def run_ours(args, rank, world, local_rank):
     barrier = grp.barrier
 
     eng = Engine(local_rank)
-    lib = eng._lib
-    ctx = eng._ctx
-    weights = eng.load_hrnet(None, WIDTH, IN_H, IN_W, seed=0)
-    frame, boxes, mats = workload()
-    P = CROPS_PER_FRAME
-    Hh, Wh = IN_H // 4, IN_W // 4
+    lib, ctx = eng._lib, eng._ctx
+    eng.load_hrnet(None, cfg["width"], cfg["in_h"], cfg["in_w"], seed=0)
+    frames, dets = synth_inputs(cfg)
+    cap, F = cfg["cap"], cfg["frames"]
+    thr = np.asarray(KEYPOINT_THRES_LIST, np.float32)
+    hts = np.asarray(HEIGHTS, np.float64)
 
-    # ---- device-resident buffers for `value`
-    d_frame = eng.to_device(frame)
-    d_mats = eng.to_device(mats.reshape(P, 6))
-    d_fi = eng.to_device(np.zeros(P, np.int32))
-    d_boxes = eng.to_device(boxes)
-    d_hcm = eng.to_device(np.full(P, 175.0))
-    d_thr = eng.to_device(np.asarray(KEYPOINT_THRES_LIST, np.float32))
-    d_crops = eng.dev_alloc(P * 3 * IN_H * IN_W * 2)
-    d_hm = eng.dev_alloc(P * 17 * Hh * Wh * 2)
-    d_kp = eng.dev_alloc(P * 17 * 2 * 4)
-    d_sc = eng.dev_alloc(P * 17 * 4)
-    d_ig = eng.dev_alloc(P * 4)
-    d_len = eng.dev_alloc(P * 11 * 4)
-    d_to = eng.dev_alloc(P * 8)
+    # ---- parameters of the chained call (the same struct for the device-resident and the host form)
+    def params(mem):
+        prm = _capi.DetPoseParams()
+        prm.n_frames, prm.h, prm.w = F, FRAME_H, FRAME_W
+        prm.persons_cap, prm.swap_rb, prm.quarter_offset, prm.mem = cap, 0, 0, mem
+        if cfg["detector"] == "yolo":
+            prm.detector, prm.person_class = _capi.DET_YOLO, 0
+            prm.N, prm.nc, prm.in_h, prm.in_w = dets[0].shape[1], dets[0].shape[2] - 5, 640, 640
+            prm.letterbox_mode, prm.max_det, prm.cand_cap, prm.conf_thres, prm.iou_thres = 0, 300, 4096, 0.4, 0.5
+        else:
+            prm.detector, prm.person_class = _capi.DET_EDET, 1
+            prm.K, prm.max_persons, prm.det_thres, prm.x_expand, prm.y_expand = 100, 16, 0.70, float(FRAME_H // 17), 0.0
+        return prm
+
+    # ---- device-resident inputs for `value`
+    d_frames = eng.to_device(frames)
+    d_dets = [eng.to_device(d) for d in dets] + [None, None]
+    prm_dev = params(DEVICE)
 
     def step_device(time_hrnet=False):
-        check(lib.hbp_crop_warp(ctx, C.c_void_p(d_frame), 1, FRAME_H, FRAME_W, C.c_void_p(d_mats), C.c_void_p(d_fi),
-                                P, IN_H, IN_W, 1, C.c_void_p(d_crops), F16, DEVICE))
-        if time_hrnet:
-            eng.timer_start(1)
-        check(lib.hbp_hrnet_forward(ctx, C.c_void_p(d_crops), P, C.c_void_p(d_hm), F16, DEVICE))
-        if time_hrnet:
-            eng.timer_stop(1)
-        check(lib.hbp_decode_proportions(ctx, C.c_void_p(d_hm), F16, P, 17, Hh, Wh, C.c_void_p(d_boxes),
-                                         C.c_void_p(d_hcm), C.c_void_p(d_thr), 0, None, C.c_void_p(d_kp),
-                                         C.c_void_p(d_sc), None, C.c_void_p(d_ig), C.c_void_p(d_len),
-                                         C.c_void_p(d_to), DEVICE))
+        tk = C.c_int(-1)
+        check(lib.hbp_det_pose_submit(ctx, C.byref(prm_dev), C.c_void_p(d_frames), ptr(d_dets[0]), ptr(d_dets[1]), ptr(d_dets[2]),
+                                      ptr(hts), hts.size, ptr(thr), C.byref(tk)))
+        return tk.value
 
-    for _ in range(max(args.warmup, 3)):          # >= 3 warm-up steps; the 2nd captures the CUDA graph
-        step_device()
+    n_out, st_out = C.c_int(0), C.c_int(0)
+
+    def collect(tk):
+        check(lib.hbp_det_pose_collect(ctx, tk, C.byref(n_out), C.byref(st_out), None, None, None, None, None, None, None, None))
+        return n_out.value
+
+    for _ in range(max(args.warmup, 3)):          # >= 3 warm-up steps; the 2nd captures the HRNet CUDA graph
+        n_live = collect(step_device())
     eng.sync()
+    assert st_out.value == 0, "pipeline status %d" % st_out.value
 
     sampler = ClockSampler(local_rank, period_ms=20) if rank == 0 else None
     barrier()
@@ -367,15 +442,16 @@ def run_ours(args, rank, world, local_rank):
     if sampler:
         sampler.mark()
     launches0 = eng.kernel_launches()
-    step_ms, hrnet_ms = [], []
+    step_ms = []
     t_wall0 = time.perf_counter()
+    crops_done = 0
     for _ in range(args.steps):
         eng.flush_l2()
         eng.timer_start(0)
-        step_device(time_hrnet=True)
+        tk = step_device()
         eng.timer_stop(0)
+        crops_done += collect(tk)
         step_ms.append(eng.timer_ms(0))
-        hrnet_ms.append(eng.timer_ms(1))
     eng.sync()
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
@@ -383,43 +459,59 @@ def run_ours(args, rank, world, local_rank):
     dev_ms_total = sum(step_ms)
     clocks = sampler.stop() if sampler else None
 
-    # ---- e2e through the public API with host buffers
-    h_frame = eng.pinned_empty(frame.shape, np.uint8)
-    h_frame[...] = frame
+    # HRNet stage alone (CUDA events around hbp_hrnet_forward on the pipeline's own crop buffer shapes), for the roofline
+    d_crops = eng.dev_alloc(cap * 3 * cfg["in_h"] * cfg["in_w"] * 2)
+    d_hm = eng.dev_alloc(cap * 17 * (cfg["in_h"] // 4) * (cfg["in_w"] // 4) * 2)
+    check(lib.hbp_memset_dev(ctx, C.c_void_p(d_crops), 0, cap * 3 * cfg["in_h"] * cfg["in_w"] * 2))
+    hrnet_ms = []
+    for i in range(3 + min(args.steps, 10)):
+        eng.flush_l2()
+        eng.timer_start(1)
+        check(lib.hbp_hrnet_forward(ctx, C.c_void_p(d_crops), cap, C.c_void_p(d_hm), F16, DEVICE))
+        eng.timer_stop(1)
+        if i >= 3:
+            hrnet_ms.append(eng.timer_ms(1))
+
+    # ---- e2e through the public API with host buffers (pinned), two batches in flight
+    h_frames = [eng.pinned_empty(frames.shape, np.uint8) for _ in range(2)]
+    h_dets = [[eng.pinned_empty(d.shape, d.dtype) for d in dets] for _ in range(2)]
+    for k in range(2):
+        h_frames[k][...] = frames
+        for a, b in zip(h_dets[k], dets):
+            a[...] = b
+
+    def submit_host(k):
+        if cfg["detector"] == "yolo":
+            return eng.det_pose_submit_yolo(h_frames[k], h_dets[k][0], person_height=HEIGHTS, persons_cap=cap, resample="bilinear")
+        return eng.det_pose_submit_edet(h_frames[k], h_dets[k][0], h_dets[k][1], h_dets[k][2], person_height=HEIGHTS,
+                                        persons_cap=cap, max_persons=16)
+
     for _ in range(3):
-        out = eng.pose_pipeline(h_frame, mats, np.zeros(P, np.int32), boxes, 175)
+        out = eng.det_pose_collect(submit_host(0))
     barrier()
-    # per-frame latency: one synchronous call per frame (upload -> kernels -> download, nothing overlapped)
-    lat = []
+    lat = []                                       # per-batch latency: one synchronous call at a time, nothing overlapped
     for _ in range(min(args.steps, 10)):
         t1 = time.perf_counter()
-        out = eng.pose_pipeline(h_frame, mats, np.zeros(P, np.int32), boxes, 175)
+        out = eng.det_pose_collect(submit_host(0))
         lat.append((time.perf_counter() - t1) * 1e3)
-    # throughput: the asynchronous form of the same call, two frames in flight -- every step still uploads its
-    # frame from pinned host memory and downloads its results; the upload of step n+1 overlaps the network of n
-    fi0 = np.zeros(P, np.int32)
-    h_frames2 = [h_frame, eng.pinned_empty(frame.shape, np.uint8)]
-    h_frames2[1][...] = frame
-    eng.pose_pipeline_collect(eng.pose_pipeline_submit(h_frame, mats, fi0, boxes, 175))
-    # a second, slower sampler for this region: every nvidia-smi query holds a driver lock that stalls launches
-    # for a while -- harmless for the event-timed steps above, visible in a wall-clock figure
-    e2e_steps = args.steps if args.steps < 5 else max(args.steps, 50)      # (tiny runs -- the ncu launch list -- stay tiny)
+    e2e_steps = args.steps if args.steps < 5 else max(args.steps, 50)
     sampler2 = ClockSampler(local_rank, period_ms=250) if rank == 0 else None
     barrier()
     if sampler2:
         sampler2.mark()
     t0 = time.perf_counter()
-    prev = None
+    prev, e2e_crops = None, 0
     for i in range(e2e_steps):
-        tk = eng.pose_pipeline_submit(h_frames2[i & 1], mats, fi0, boxes, 175)
+        tk = submit_host(i & 1)
         if prev is not None:
-            out = eng.pose_pipeline_collect(prev)
+            e2e_crops += eng.det_pose_collect(prev)["n"]
         prev = tk
-    out = eng.pose_pipeline_collect(prev)
+    out = eng.det_pose_collect(prev, return_heatmaps=True)
+    e2e_crops += out["n"]
     e2e_s = time.perf_counter() - t0
     barrier()
-    h2d = frame.nbytes + P * (48 + 8 + 16 + 4) + 32 * 4
-    d2h = sum(v.nbytes for v in out.values())
+    h2d = frames.nbytes + sum(d.nbytes for d in dets) + hts.nbytes + 17 * 4 + 64
+    d2h = 64 + cap * (8 + 4 + 16 + 17 * 8 + 17 * 4 + 4 + 44)
     if sampler2:
         c2 = sampler2.stop()
         if clocks and c2.get("samples"):
@@ -429,19 +521,24 @@ def run_ours(args, rank, world, local_rank):
     # ---- max over ranks (device time, e2e wall time)
     dev_ms_total, e2e_s, wall_ms = grp.max_over_ranks([dev_ms_total, e2e_s, wall_ms])
     launches = int(grp.sum_over_ranks([launches])[0])
+    crops_all = grp.sum_over_ranks([crops_done, e2e_crops])
     if rank != 0:
         grp.close()
         return
 
-    # ---- per-stage timings on the detector-head shapes (configs[2]), device-resident
+    parity = check_against_oracle(out, HEIGHTS)
+
+    # ---- per-stage timings on the detector-head shapes, device-resident (informational)
     stages = {}
     try:
-        pred, _ = synth.yolo_decoded_head()
+        from human_body_proportion_estimation_b200 import synth
+        pred = synth.yolo_decoded_head()[0]
         d_pred = eng.to_device(pred)
         d_det = eng.dev_alloc(300 * 6 * 4)
         d_cnt = eng.dev_alloc(4)
         d_cls = eng.to_device(np.zeros(1, np.int32))
         d_lb = eng.dev_alloc(3 * 640 * 640 * 2)
+        d_frame1 = d_frames                                   # first frame
 
         def timed(fn, reps=20):
             fn(); eng.sync()
@@ -452,67 +549,120 @@ def run_ours(args, rank, world, local_rank):
             return eng.timer_ms(2) / reps
 
         stages["letterbox_1080p_to_640_f16"] = timed(lambda: check(lib.hbp_preprocess(
-            ctx, C.c_void_p(d_frame), 1, FRAME_H, FRAME_W, PRE_LETTERBOX, 640, 640, 1, 128, C.c_void_p(d_lb), F16, NCHW, DEVICE)))
+            ctx, C.c_void_p(d_frame1), 1, FRAME_H, FRAME_W, PRE_LETTERBOX, 640, 640, 1, 128, C.c_void_p(d_lb), F16, NCHW, DEVICE)))
         stages["letterbox_pil_bicubic_1080p_to_640_f16"] = timed(lambda: check(lib.hbp_preprocess(
-            ctx, C.c_void_p(d_frame), 1, FRAME_H, FRAME_W, PRE_LETTERBOX_PIL, 640, 640, 1, 128, C.c_void_p(d_lb), F16, NCHW, DEVICE)))
+            ctx, C.c_void_p(d_frame1), 1, FRAME_H, FRAME_W, PRE_LETTERBOX_PIL, 640, 640, 1, 128, C.c_void_p(d_lb), F16, NCHW, DEVICE)))
         stages["yolo_nms_25200x85_person"] = timed(lambda: check(lib.hbp_yolo_nms(
             ctx, C.c_void_p(d_pred), 1, 25200, 80, 0.4, 0.5, C.c_void_p(d_cls), 1, 300, C.c_void_p(d_det), C.c_void_p(d_cnt), DEVICE)))
-        stages["crop_64x256x192_f16"] = timed(lambda: check(lib.hbp_crop_warp(
-            ctx, C.c_void_p(d_frame), 1, FRAME_H, FRAME_W, C.c_void_p(d_mats), C.c_void_p(d_fi), P, IN_H, IN_W, 1,
-            C.c_void_p(d_crops), F16, DEVICE)))
-        stages["decode_proportions_64x17x64x48_f16"] = timed(lambda: check(lib.hbp_decode_proportions(
-            ctx, C.c_void_p(d_hm), F16, P, 17, Hh, Wh, C.c_void_p(d_boxes), C.c_void_p(d_hcm), C.c_void_p(d_thr), 0,
-            None, C.c_void_p(d_kp), C.c_void_p(d_sc), None, C.c_void_p(d_ig), C.c_void_p(d_len), C.c_void_p(d_to), DEVICE)))
-        stages["hrnet_w32_64crops"] = statistics.mean(hrnet_ms)
+        stages["hrnet_w%d_%dslots" % (cfg["width"], cap)] = statistics.mean(hrnet_ms)
+        stages["chain_total"] = dev_ms_total / args.steps
+        stages["chain_minus_hrnet (letterbox + NMS + person params + crop + decode + result copy)"] = dev_ms_total / args.steps - statistics.mean(hrnet_ms)
     except Exception as e:           # stage timings are informational
         stages["error"] = str(e)
 
     pk = peaks()
-    flops_crop, _ = hrnet_arch.flops_per_crop(WIDTH, IN_H, IN_W)
+    flops_crop, _ = hrnet_arch.flops_per_crop(cfg["width"], cfg["in_h"], cfg["in_w"])
     hr_ms = statistics.mean(hrnet_ms)
-    achieved = flops_crop * P / (hr_ms * 1e-3) / 1e12
-    n_conv_launch = max(1, int(launches) // max(1, world) // args.steps - 2)     # HRNet launches per step
-    value = world * P * args.steps / (dev_ms_total * 1e-3)
-    e2e_val = world * P * e2e_steps / e2e_s
+    achieved = flops_crop * cap / (hr_ms * 1e-3) / 1e12
+    n_launch_step = max(1, int(launches) // max(1, world) // args.steps)
+    value = crops_all[0] / (dev_ms_total * 1e-3)
+    e2e_val = crops_all[1] / e2e_s
 
     stage_rf = None
+    cpu = None
     if world == 1:
         try:
             stage_rf = stage_rooflines(eng, pk["hbm"])
         except Exception as e:
             stage_rf = {"error": str(e)}
-
-    cpu = None
-    if world == 1:          # the CPU baseline is timed on rank 0 at N = 1 only
-        try:
-            cv, cms, cores, note = cpu_reference_run(8, 2, 1, weights)
-            cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port", "sample": note + "; 2 timed steps"}
+        try:          # the CPU baseline is timed on rank 0 at N = 1 only, one or two full batches of the same workload
+            cv, cms, cores, note = cpu_reference_run(cfg, 2 if cfg["width"] == 32 else 1, 1, frames, dets)
+            cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port", "sample": note}
         except Exception as e:
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+
+    stream = None
+    if args.config == 1:
+        try:          # the product's one-process multi-GPU API on BASELINE configs[4] (4K stream, 100 persons per frame)
+            stream = stream_config4(world)
+        except Exception as e:
+            stream = {"error": str(e)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": config_dict(),
+        "config": config_dict(cfg),
+        "crops_per_step_per_gpu": n_live,
         "wall_ms_per_step": wall_ms / args.steps,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "p50_frame_latency_ms": statistics.median(lat), "steps": e2e_steps,
-                "api": "Engine.pose_pipeline_submit/_collect (hbp_pose_pipeline_submit/_collect), two frames in flight; latency from the synchronous Engine.pose_pipeline"},
+                "p50_batch_latency_ms": statistics.median(lat), "steps": e2e_steps,
+                "api": "Engine.det_pose_submit_%s / det_pose_collect (hbp_det_pose_submit/_collect), two batches in flight; latency from one synchronous submit+collect at a time" % cfg["detector"]},
+        "parity_check": parity,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "HRNet conv stack: %d launches per step (conv_umma_halo_kernel, conv_umma_pgroup_kernel (one per fuse level), conv_umma_kernel, upsample_add_group, stem, head), one CUDA graph" % n_conv_launch,
+        "roofline": {"bound": "tensor", "kernel": "HRNet conv stack (conv_umma_halo_kernel, conv_umma_pgroup_kernel, conv_umma_kernel, upsample_add_group, stem, head; one CUDA graph), %d person slots; the whole chain is %d launches per step" % (cap, n_launch_step),
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                      "peak_source": pk["src"], "traffic": hrnet_traffic().get("dram_bytes_per_launch"),
                      "traffic_note": hrnet_traffic().get("note"),
-                     "flop_per_launch_avg": flops_crop * P / n_conv_launch,
-                     "launch_ms_avg": hr_ms / n_conv_launch, "hrnet_ms": hr_ms},
+                     "flop_per_step": flops_crop * cap, "hrnet_ms": hr_ms},
         "cpu_baseline": cpu,
         "stages_ms": stages,
         "stage_rooflines": stage_rf,
+        "stream_config4": stream,
         "clocks": clocks,
     }
     emit(json.dumps(line))
     grp.close()
+
+
+def stream_config4(n_gpus, frames=160, warmup=16, persons=100):
+    """BASELINE configs[4] through MultiGpuEngine.stream in ONE process over `n_gpus` GPUs (frame f -> GPU f mod G, two
+    frames in flight per GPU, one host thread per GPU)."""
+    from human_body_proportion_estimation_b200 import geometry, synth
+    from human_body_proportion_estimation_b200.engine import MultiGpuEngine
+    H, W = 2160, 3840
+    mg = MultiGpuEngine(list(range(n_gpus)), width=32, in_h=256, in_w=192, seed=0)
+    base = [synth.frame_u8(H, W, seed=synth.SEED_BASE + 50 + i, smooth=False) for i in range(4)]
+    pinned = []
+    for e in mg.engines:
+        bufs = []
+        for b in base:
+            p = e.pinned_empty(b.shape, np.uint8)
+            p[...] = b
+            bufs.append(p)
+        pinned.append(bufs)
+    sets = []
+    for i in range(4):
+        boxes = synth.person_boxes_yxyx_px(persons, H, W, seed=synth.SEED_BASE + 60 + i, hmin=150, hmax=600)
+        mats = geometry.crop_and_resize_matrices(boxes / np.array([H, W, H, W], np.float32), H, W, 256, 192)
+        sets.append((mats.reshape(-1, 6), boxes))
+    G = n_gpus
+
+    def source(f):
+        mats, boxes = sets[f % 4]
+        return pinned[f % G][(f // G) % 4], mats, boxes, 175.0
+
+    n = frames * G
+    mg.stream(source, warmup * G)
+    t0 = time.perf_counter()
+    res, lat = mg.stream(source, n)
+    dt = time.perf_counter() - t0
+    # the synchronous latency: one frame at a time on GPU 0 (submit -> collect, nothing else in flight)
+    e0 = mg.engines[0]
+    sync_lat = []
+    for f in range(8):
+        fr, mats, boxes, h = source(f * G)
+        t1 = time.perf_counter()
+        e0.pose_pipeline_collect(e0.pose_pipeline_submit(fr, mats, np.zeros(persons, np.int32), boxes, h))
+        sync_lat.append((time.perf_counter() - t1) * 1e3)
+    lat = np.sort(np.asarray(lat))
+    for e in mg.engines:
+        e.close()
+    return {"workload": "configs[4]: 4K frames (2160x3840x3 u8, pinned), %d persons/frame, HRNet-W32 256x192, ONE process, frame f -> GPU f mod G" % persons,
+            "n_gpus": G, "frames": n, "crops_per_s": n * persons / dt, "frames_per_s": n / dt,
+            "p50_frame_latency_ms_two_in_flight": float(lat[len(lat) // 2]), "p95_frame_latency_ms_two_in_flight": float(lat[int(len(lat) * 0.95)]),
+            "p50_frame_latency_ms_synchronous": float(np.median(sync_lat)),
+            "api": "MultiGpuEngine.stream (hbp_pose_pipeline_submit/_collect)"}
 
 
 _REAL_STDOUT = None
@@ -539,6 +689,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -550,7 +701,7 @@ def main():
         # not under torchrun: relaunch one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
-               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--config", str(args.config)]
         sys.exit(subprocess.call(cmd))
     run_ours(args, rank, world, local_rank)
 

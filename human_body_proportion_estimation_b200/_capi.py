@@ -64,6 +64,7 @@ _SIGS = {
     "hbp_preprocess": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I]),
     "hbp_yolo_decode_raw": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I]),
     "hbp_yolo_nms": (_I, [_P, _P, _I, _I, _I, C.c_float, C.c_double, _P, _I, _I, _P, _P, _I]),
+    "hbp_yolo_filter": (_I, [_P, _P, _I, _I, _I, C.c_float, _P, _I, _I, _P, _I]),
     "hbp_yolo_nms_legacy": (_I, [_P, _P, _I, _I, _I, C.c_float, C.c_float, _I, _P, _P, _I]),
     "hbp_scale_coords": (_I, [_P, _P, _I, _I, _I, _I, _I, _I]),
     "hbp_edet_person_filter": (_I, [_P, _P, _P, _P, _I, _I, C.c_float, C.c_float, C.c_float,

@@ -240,6 +240,22 @@ int hbp_yolo_nms(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float co
     return st.finish();
 }
 
+int hbp_yolo_filter(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, const int* classes, int n_classes,
+                    int cand_cap, int* out_count, int mem) {
+    BIND(ctx);
+    HBP_REQUIRE(pred && out_count && B > 0 && N > 0 && nc > 0 && cand_cap > 0, "bad shape");
+    HBP_REQUIRE(n_classes >= 0 && (n_classes == 0 || classes), "bad class filter");
+    Stager st(ctx, mem);
+    const float* d_pred = st.in(pred, (size_t)B * N * (5 + nc), SC_IN0);
+    const int* d_cls = st.in(classes, (size_t)n_classes, SC_IN1);
+    int* d_cnt = st.out(out_count, (size_t)B, SC_OUT1);
+    if (st.status) return st.status;
+    int s = k_yolo_filter(ctx, d_pred, B, N, nc, conf, d_cls, n_classes, cand_cap, d_cnt);
+    if (s) return s;
+    st.back(out_count, d_cnt, (size_t)B);
+    return st.finish();
+}
+
 int hbp_yolo_nms_legacy(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, float thr,
                         int max_out, float* out_det, int* out_count, int mem) {
     BIND(ctx);

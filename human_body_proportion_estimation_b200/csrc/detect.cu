@@ -68,6 +68,8 @@ yolo_decode_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
 }
 
 // ---- candidates ---------------------------------------------------------------
+constexpr int kFilterUnroll = 4;
+
 struct Cand {           // 32 bytes
     float x1, y1, x2, y2;
     float conf;         // official: obj*cls ; legacy: obj
@@ -84,16 +86,22 @@ yolo_filter_kernel(const float* __restrict__ pred, int N, int nc, float conf_thr
     const int E = 5 + nc;
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int row0 = warp_global * 32;
-    if (row0 >= N) return;
+    const int row00 = warp_global * (32 * kFilterUnroll);
+    if (row00 >= N) return;
     const float* __restrict__ base = pred + (size_t)b * N * E;
-    const int my_row = row0 + lane;
-    float obj = 0.f;
-    bool flag = false;
-    if (my_row < N) {
-        obj = __ldg(base + (size_t)my_row * E + 4);
-        flag = legacy ? (obj >= conf_thres) : (obj > conf_thres);
+    // kFilterUnroll groups of 32 rows per warp: all objectness loads (one 32-byte sector of a 340-byte row each) are in
+    // flight before the first ballot -- the kernel is bound by the latency of these strided loads, not by bytes
+    float objs[kFilterUnroll];
+#pragma unroll
+    for (int u = 0; u < kFilterUnroll; ++u) {
+        const int my_row = row00 + 32 * u + lane;
+        objs[u] = my_row < N ? __ldg(base + (size_t)my_row * E + 4) : 0.f;
     }
+#pragma unroll
+    for (int u = 0; u < kFilterUnroll; ++u) {
+    const int row0 = row00 + 32 * u;
+    const float obj = objs[u];
+    const bool flag = (row0 + lane < N) && (legacy ? (obj >= conf_thres) : (obj > conf_thres));
     unsigned todo = __ballot_sync(0xffffffffu, flag);
     while (todo) {
         const int l = __ffs(todo) - 1;
@@ -147,6 +155,7 @@ yolo_filter_kernel(const float* __restrict__ pred, int N, int nc, float conf_thr
             }
         }
     }
+    }
 }
 
 // does candidate a come before candidate b in the output order?
@@ -162,32 +171,28 @@ struct SortedBox {      // 32 bytes
     int cand;               // index into the candidate list
 };
 
-__global__ void __launch_bounds__(256)
+// One WARP per candidate: its lanes split the other candidates, count the ones that precede it and reduce -- n / 8 CTAs
+// of eight warps (150 for the 1200 candidates of a 25200-row head) instead of n / 256 CTAs whose every thread walked all n.
+constexpr int kRankWarps = 8;
+__global__ void __launch_bounds__(32 * kRankWarps)
 rank_scatter_kernel(const Cand* __restrict__ cand, const int* __restrict__ cand_count, int cap,
                     int legacy, int max_nms, float max_wh, SortedBox* __restrict__ sorted,
                     int* __restrict__ n_sorted) {
-    __shared__ float s_conf[256], s_cls[256];
-    __shared__ int s_src[256];
     const int b = blockIdx.y;
     const int n = min(cand_count[b], cap);
     const Cand* __restrict__ c = cand + (size_t)b * cap;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x * blockDim.x >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kRankWarps + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) n_sorted[b] = min(n, max_nms);
-    Cand me{};
-    if (i < n) me = c[i];
+    if (i >= n) return;
+    const Cand me = c[i];
     int rank = 0;
-    for (int t0 = 0; t0 < n; t0 += 256) {
-        const int j = t0 + threadIdx.x;
-        if (j < n) { s_conf[threadIdx.x] = c[j].conf; s_cls[threadIdx.x] = c[j].cls; s_src[threadIdx.x] = c[j].src; }
-        __syncthreads();
-        const int m = min(256, n - t0);
-        if (i < n)
-            for (int k = 0; k < m; ++k)
-                rank += precedes(s_conf[k], s_cls[k], s_src[k], me.conf, me.cls, me.src, legacy) ? 1 : 0;
-        __syncthreads();
+    for (int j = lane; j < n; j += 32) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(c + j) + 1);      // conf, cls, aux, src
+        rank += precedes(q.x, q.y, __float_as_int(q.w), me.conf, me.cls, me.src, legacy) ? 1 : 0;
     }
-    if (i < n && rank < max_nms) {
+    rank = __reduce_add_sync(0xffffffffu, rank);
+    if (lane == 0 && rank < max_nms) {
         SortedBox s;
         // onnx_utils.py:202-204: boxes + cls * max_wh (float32 mul, float32 add)
         const float off = legacy ? 0.f : __fmul_rn(me.cls, max_wh);
@@ -305,6 +310,58 @@ nms_sweep_kernel(const uint32_t* __restrict__ mask, const int* __restrict__ n_so
     if (threadIdx.x == 0) keep_count[b] = s_kept;
 }
 
+// Sweep for n <= 4096 boxes (128 mask words) in ONE warp: lane l keeps the removed-words l, l+32, l+64, l+96 in registers,
+// so the walk over the words needs no block barrier; per word: the 32 diagonal words (one per lane, requested one word
+// ahead), the in-warp resolution of the word's 32 boxes with shuffles, then one coalesced 128-byte row read per kept box.
+constexpr int kWarpSweepWords = 128;
+__global__ void __launch_bounds__(32)
+nms_sweep_warp_kernel(const uint32_t* __restrict__ mask, const int* __restrict__ n_sorted,
+                      int words_cap, size_t mask_img_stride, int max_keep, int* __restrict__ keep,
+                      int* __restrict__ keep_count) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int n = n_sorted[b];
+    const int words = (n + 31) >> 5;
+    const uint32_t* __restrict__ m = mask + (size_t)b * mask_img_stride;
+    uint32_t rem[4] = {0u, 0u, 0u, 0u};
+    int kept = 0;
+    uint32_t diag_next = (lane < n) ? m[(size_t)lane * words_cap] : 0u;
+    for (int w = 0; w < words && kept < max_keep; ++w) {
+        const uint32_t diag = diag_next;
+        if (w + 1 < words) {
+            const int i1 = (w + 1) * 32 + lane;
+            diag_next = (i1 < n) ? m[(size_t)i1 * words_cap + (w + 1)] : 0u;
+        }
+        const int wq = w >> 5;
+        const uint32_t mine_w = wq == 0 ? rem[0] : wq == 1 ? rem[1] : wq == 2 ? rem[2] : rem[3];     // (no run-time register-array index)
+        uint32_t removed = __shfl_sync(0xffffffffu, mine_w, w & 31);
+        if (n - w * 32 < 32) removed |= ~0u << (n - w * 32);     // padding bits
+        uint32_t keepbits = 0;
+        for (int l = 0; l < 32; ++l) {
+            const uint32_t dl = __shfl_sync(0xffffffffu, diag, l);
+            if (!((removed >> l) & 1u) && kept < max_keep) {
+                keepbits |= 1u << l;
+                removed |= dl;
+                ++kept;
+            } else {
+                removed |= 1u << l;
+            }
+        }
+        // (keepbits / kept are warp-uniform: every lane ran the same loop on shuffled values)
+        int kk = kept - __popc(keepbits);
+        for (uint32_t t = keepbits; t; t &= t - 1) {
+            const int row = w * 32 + __ffs(t) - 1;
+            if (lane == 0) keep[(size_t)b * max_keep + kk] = row;
+            ++kk;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int ww = lane + 32 * q;
+                if (ww > w && ww < words) rem[q] |= m[(size_t)row * words_cap + ww];
+            }
+        }
+    }
+    if (lane == 0) keep_count[b] = kept;
+}
+
 __global__ void nms_gather_kernel(const SortedBox* __restrict__ sorted, const Cand* __restrict__ cand,
                                   int cap, const int* __restrict__ keep, const int* __restrict__ keep_count,
                                   const int* __restrict__ cand_count, int max_keep, int legacy,
@@ -373,7 +430,7 @@ int run_nms(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, d
     int* cand_count = misc, *n_sorted = misc + B, *keep_count = misc + 2 * B, *keep = misc + 3 * B;
     HBP_CUDA(cudaMemsetAsync(misc, 0, (size_t)3 * B * sizeof(int), ctx->stream));
     {
-        const int warps = (N + 31) / 32;
+        const int warps = (N + 32 * kFilterUnroll - 1) / (32 * kFilterUnroll);
         dim3 grid((warps + 7) / 8, B);
         yolo_filter_kernel<<<grid, 256, 0, ctx->stream>>>(pred, N, nc, conf, legacy, classes, n_classes, cand, cand_count, cap);
         HBP_LAUNCH_CHECK(ctx);
@@ -388,8 +445,8 @@ int run_nms(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, d
     for (int b = 0; b < B; ++b) n_max = max(n_max, min(h_counts[b], cap));
     n_max = min(n_max, max_nms);
     if (n_max > 0) {
-        dim3 g1((n_max + 255) / 256, B);
-        rank_scatter_kernel<<<g1, 256, 0, ctx->stream>>>(cand, cand_count, cap, legacy, max_nms, 4096.f, sorted, n_sorted);
+        dim3 g1((n_max + kRankWarps - 1) / kRankWarps, B);
+        rank_scatter_kernel<<<g1, 32 * kRankWarps, 0, ctx->stream>>>(cand, cand_count, cap, legacy, max_nms, 4096.f, sorted, n_sorted);
         HBP_LAUNCH_CHECK(ctx);
         const int words = (n_max + 31) / 32;
         const size_t mask_img_stride = (size_t)n_max * words;
@@ -398,7 +455,10 @@ int run_nms(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, d
         dim3 g2(words, min((n_max + 7) / 8, 1024), B);
         nms_mask_kernel<<<g2, 256, 0, ctx->stream>>>(sorted, n_sorted, cap, words, mask_img_stride, thr, legacy, mask);
         HBP_LAUNCH_CHECK(ctx);
-        nms_sweep_kernel<<<B, kSweepThreads, 0, ctx->stream>>>(mask, n_sorted, words, mask_img_stride, max_keep, keep, keep_count);
+        if (words <= kWarpSweepWords)
+            nms_sweep_warp_kernel<<<B, 32, 0, ctx->stream>>>(mask, n_sorted, words, mask_img_stride, max_keep, keep, keep_count);
+        else
+            nms_sweep_kernel<<<B, kSweepThreads, 0, ctx->stream>>>(mask, n_sorted, words, mask_img_stride, max_keep, keep, keep_count);
         HBP_LAUNCH_CHECK(ctx);
     }
     nms_gather_kernel<<<B, 128, 0, ctx->stream>>>(sorted, cand, cap, keep, keep_count, cand_count, max_keep, legacy, out_det, out_count);
@@ -429,19 +489,22 @@ int run_nms_bounded(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float
     int* cand_count = misc, *n_sorted = misc + B, *keep_count = misc + 2 * B, *keep = misc + 3 * B;
     HBP_CUDA(cudaMemsetAsync(misc, 0, (size_t)3 * B * sizeof(int), ctx->stream));
     {
-        const int warps = (N + 31) / 32;
+        const int warps = (N + 32 * kFilterUnroll - 1) / (32 * kFilterUnroll);
         dim3 grid((warps + 7) / 8, B);
         yolo_filter_kernel<<<grid, 256, 0, ctx->stream>>>(pred, N, nc, conf, 0, classes, n_classes, cand, cand_count, cap);
         HBP_LAUNCH_CHECK(ctx);
     }
     if (status) { nms_overflow_kernel<<<(B + 63) / 64, 64, 0, ctx->stream>>>(cand_count, cap, B, status); HBP_LAUNCH_CHECK(ctx); }
-    dim3 g1((cap + 255) / 256, B);
-    rank_scatter_kernel<<<g1, 256, 0, ctx->stream>>>(cand, cand_count, cap, 0, 30000, 4096.f, sorted, n_sorted);
+    dim3 g1((cap + kRankWarps - 1) / kRankWarps, B);
+    rank_scatter_kernel<<<g1, 32 * kRankWarps, 0, ctx->stream>>>(cand, cand_count, cap, 0, 30000, 4096.f, sorted, n_sorted);
     HBP_LAUNCH_CHECK(ctx);
     dim3 g2(words, 16, B);
     nms_mask_kernel<<<g2, 256, 0, ctx->stream>>>(sorted, n_sorted, cap, words, mask_img_stride, thr, 0, mask);
     HBP_LAUNCH_CHECK(ctx);
-    nms_sweep_kernel<<<B, kSweepThreads, 0, ctx->stream>>>(mask, n_sorted, words, mask_img_stride, max_keep, keep, keep_count);
+    if (words <= kWarpSweepWords)
+        nms_sweep_warp_kernel<<<B, 32, 0, ctx->stream>>>(mask, n_sorted, words, mask_img_stride, max_keep, keep, keep_count);
+    else
+        nms_sweep_kernel<<<B, kSweepThreads, 0, ctx->stream>>>(mask, n_sorted, words, mask_img_stride, max_keep, keep, keep_count);
     HBP_LAUNCH_CHECK(ctx);
     nms_gather_kernel<<<B, 128, 0, ctx->stream>>>(sorted, cand, cap, keep, keep_count, cand_count, max_keep, 0, out_det, out_count);
     HBP_LAUNCH_CHECK(ctx);
@@ -533,6 +596,18 @@ persons_from_edet_kernel(const float* __restrict__ boxes_n, const int* __restric
 }
 
 }  // namespace
+
+int k_yolo_filter(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, const int* classes, int n_classes,
+                  int cand_cap, int* out_count) {
+    Cand* cand = (Cand*)hbp_scratch(ctx, SC_NMS_CAND, (size_t)B * cand_cap * sizeof(Cand));
+    if (!cand) return HBP_ERR_NOMEM;
+    HBP_CUDA(cudaMemsetAsync(out_count, 0, (size_t)B * sizeof(int), ctx->stream));
+    const int warps = (N + 32 * kFilterUnroll - 1) / (32 * kFilterUnroll);
+    dim3 grid((warps + 7) / 8, B);
+    yolo_filter_kernel<<<grid, 256, 0, ctx->stream>>>(pred, N, nc, conf, 0, classes, n_classes, cand, out_count, cand_cap);
+    HBP_LAUNCH_CHECK(ctx);
+    return HBP_OK;
+}
 
 int k_yolo_nms_bounded(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, double iou,
                        const int* classes, int n_classes, int max_det, int cand_cap, float* out_det, int* out_count,

@@ -152,6 +152,8 @@ int k_decode_proportions(hbp_ctx*, const void* hm, int dtype, int P, int J, int 
                          int32_t* idx, uint32_t* ignored, float* lengths, double* torso,
                          const int* live = nullptr,          // optional device count, slots >= *live are skipped
                          const double* Maff = nullptr, int crop_h = 0, int crop_w = 0);   // optional (P,6) dst->src matrices: general inverse-affine remap
+int k_yolo_filter(hbp_ctx*, const float* pred, int B, int N, int nc, float conf, const int* classes, int n_classes,
+                  int cand_cap, int* out_count);
 int k_yolo_nms_bounded(hbp_ctx*, const float* pred, int B, int N, int nc, float conf, double iou,
                        const int* classes, int n_classes, int max_det, int cand_cap, float* out_det, int* out_count,
                        int* status);

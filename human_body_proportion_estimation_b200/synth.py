@@ -113,3 +113,39 @@ def edet_outputs(n_frames=16, n_persons=16, img_h=1080, img_w=1920, seed=SEED_BA
         s[person_rows] = np.maximum(s[person_rows], np.float32(0.75))
         boxes[f], scores[f], classes[f] = b, s, c
     return boxes, scores, classes
+
+
+def yolo_head_grid(n_cols=16, n_rows=4, N=25200, nc=80, seed=SEED_BASE + 8, in_size=640, content=(140, 500)):
+    """Config 2 head for a fixed person count: decoded YOLOv5 head (1,N,5+nc) f32 whose NMS keeps exactly
+    n_cols*n_rows persons (64): one person per cell of a grid over the letterboxed content rows, ~12 firing anchors
+    each (xywh jitter sigma 1 px), background obj~U[0,0.05], 200 non-person distractors.  Returns (pred, boxes_xywh)."""
+    rng = np.random.default_rng(seed)
+    pred = np.empty((1, N, 5 + nc), np.float32)
+    pred[0, :, 0:2] = rng.uniform(0, in_size, (N, 2))
+    pred[0, :, 2:4] = rng.uniform(8, 200, (N, 2))
+    pred[0, :, 4] = rng.uniform(0, 0.05, N)
+    pred[0, :, 5:] = rng.uniform(0, 0.2, (N, nc))
+    free = rng.permutation(N)
+    pos = 0
+    cw, chh = in_size / n_cols, (content[1] - content[0]) / n_rows
+    planted = []
+    for r in range(n_rows):
+        for c in range(n_cols):
+            w = rng.uniform(0.55 * cw, 0.8 * cw)
+            h = rng.uniform(0.65 * chh, 0.88 * chh)
+            cx, cy = (c + 0.5) * cw, content[0] + (r + 0.5) * chh
+            planted.append((cx, cy, w, h))
+            k = 12
+            rows = free[pos:pos + k]
+            pos += k
+            pred[0, rows, 0] = cx + rng.normal(0, 1, k)
+            pred[0, rows, 1] = cy + rng.normal(0, 1, k)
+            pred[0, rows, 2] = w + rng.normal(0, 1, k)
+            pred[0, rows, 3] = h + rng.normal(0, 1, k)
+            pred[0, rows, 4] = rng.uniform(0.6, 1.0, k)
+            pred[0, rows, 5] = rng.uniform(0.9, 1.0, k)
+    rows = free[pos:pos + 200]
+    pred[0, rows, 4] = rng.uniform(0.45, 1.0, len(rows))
+    cls = rng.integers(1, nc, len(rows))
+    pred[0, rows, 5 + cls] = rng.uniform(0.9, 1.0, len(rows))
+    return pred, np.asarray(planted, np.float32)

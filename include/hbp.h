@@ -118,6 +118,13 @@ HBP_API int hbp_yolo_nms(hbp_ctx* ctx, const float* pred, int B, int N, int nc,
                  float conf_thres, double iou_thres, const int* classes, int n_classes,
                  int max_det, float* out_det, int* out_count, int mem);
 
+/* K2 alone: the candidate filter of non_max_suppression (hble/modules/onnx_utils.py:133,168-187: obj > conf, best
+ * class of cls*obj > conf, optional class filter) on pred (B,N,5+nc) f32.  out_count (B) int32 = candidates per
+ * image (capped at cand_cap); the candidates themselves stay in the library's scratch for hbp_yolo_nms-style
+ * post-processing.  The stage's roofline probe (bench.py). */
+HBP_API int hbp_yolo_filter(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf_thres,
+                    const int* classes, int n_classes, int cand_cap, int* out_count, int mem);
+
 /* Legacy per-class greedy NMS with the +1 pixel IoU: replaces
  * hble/modules/onnx_utils.py:39-95 (w_non_max_suppression + w_bbox_iou).
  * out_det: (B,max_out,7) rows [x1,y1,x2,y2,obj,cls_conf,cls] grouped by class
