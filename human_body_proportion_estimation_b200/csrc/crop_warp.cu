@@ -27,7 +27,8 @@
 
 namespace {
 
-constexpr int kBandRows = 8;
+constexpr int kBandRows = 32;             // output rows per CTA: the per-CTA tables (column deltas, tap offsets, x weights) are built once per band
+constexpr int kPassRows = 8;              // ... and the band is sampled in passes of <= 8 rows whose source rows fit the shared-memory budget
 constexpr int kThreads = 256;
 constexpr int kSmemBudget = 28 * 1024;    // per CTA: 7 CTAs of 256 threads per SM
 constexpr int kSmemPad = 16;              // bytes in front of / behind the staged box: a zero-weight tap may read up to 3 bytes outside it
@@ -80,7 +81,7 @@ template <> __device__ __forceinline__ __half finish_acc<__half>(unsigned bits) 
 }
 
 template <typename OutT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
                  const double* __restrict__ Ms, const int* __restrict__ frame_idx, int P,
                  int out_h, int out_w, int swap_rb, OutT* __restrict__ out, const int* __restrict__ live) {
@@ -142,33 +143,42 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
         const int srows = axis ? min(nrows, 2 * nr) : nrows;
         *need = (cols > 0 && nrows > 0) ? (long long)srows * (((long long)cols * 3 + 15 + 15) / 16 * 16) : 0;
     };
-    if (threadIdx.x == 0) {
-        int rp = kBandRows;
-        for (; rp > 1; rp >>= 1) {
-            int box[4];
-            long long need;
-            box_of(row0, min(rp, rows), box, &need);
-            if (need <= kSmemBudget) break;
-        }
-        s_rp = rp;
+    // (all box arithmetic is double precision, slow on this part: spread it over threads instead of leaving 255 threads
+    // at a barrier behind thread 0 -- the round-1 profile had stall_barrier on top)
+    __shared__ int s_fit[4];
+    __shared__ int s_pbox[kBandRows][5];    // per pass: x0, y0, cols, rows, staged?
+    if (threadIdx.x < 4) {
+        const int rp_t = kPassRows >> threadIdx.x;      // 8, 4, 2, 1
+        int box[4];
+        long long need;
+        box_of(row0, min(rp_t, rows), box, &need);
+        s_fit[threadIdx.x] = need <= kSmemBudget ? 1 : 0;
     }
     __syncthreads();
+    if (threadIdx.x == 0) s_rp = s_fit[0] ? 8 : s_fit[1] ? 4 : s_fit[2] ? 2 : 1;
+    __syncthreads();
     const int rp = s_rp;
+    {
+        const int n_pass = (rows + rp - 1) / rp;
+        if ((int)threadIdx.x < n_pass) {
+            const int pr0_t = row0 + (int)threadIdx.x * rp;
+            int box[4];
+            long long need;
+            box_of(pr0_t, min(rp, row0 + rows - pr0_t), box, &need);
+            s_pbox[threadIdx.x][0] = box[0]; s_pbox[threadIdx.x][1] = box[1]; s_pbox[threadIdx.x][2] = box[2]; s_pbox[threadIdx.x][3] = box[3];
+            s_pbox[threadIdx.x][4] = (box[2] > 0 && box[3] > 0 && need <= kSmemBudget) ? 1 : 0;
+        }
+    }
+    __syncthreads();
     const int groups = (out_w + 7) / 8;                 // 8 output pixels per thread-iteration
     const size_t plane = (size_t)out_h * out_w;
     OutT* __restrict__ obase = out + (size_t)p * 3 * plane;
+    bool tables_built = false;
     for (int pr0 = row0; pr0 < row0 + rows; pr0 += rp) {
     const int prow = min(rp, row0 + rows - pr0);
-    if (threadIdx.x == 0) {
-        int box[4];
-        long long need;
-        box_of(pr0, prow, box, &need);
-        s_box[0] = box[0]; s_box[1] = box[1]; s_box[2] = box[2]; s_box[3] = box[3];
-        s_use_smem = (box[2] > 0 && box[3] > 0 && need <= kSmemBudget) ? 1 : 0;
-    }
-    __syncthreads();
-    const int bx0 = s_box[0], by0 = s_box[1], bcols = s_box[2], brows = s_box[3];
-    const bool staged = s_use_smem != 0;
+    const int* pb = s_pbox[(pr0 - row0) / rp];
+    const int bx0 = pb[0], by0 = pb[1], bcols = pb[2], brows = pb[3];
+    const bool staged = pb[4] != 0;
     const int pitch = ((bcols * 3 + 15 + 15) / 16) * 16;   // bytes per staged row
 
     const bool slots = staged && axis && brows > 2 * prow;      // staged row 2*ry + t = source row of tap t of output row pr0 + ry
@@ -182,7 +192,9 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
         }
         __syncthreads();
     }
-    if (staged && axis) {
+    if (staged && axis && !tables_built) {
+        // (an axis-aligned map has the same source column range in every row: one table per band)
+        tables_built = true;
         const int X0c = __double2int_rn(__dmul_rn(A.m02, 1024.0)) + 16;
         for (int x = threadIdx.x; x < ((out_w + 7) & ~7); x += kThreads) {
             const int X = (X0c + s_ad[min(x, out_w - 1)]) >> 5;
@@ -199,33 +211,59 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
         // sub-16 phase `ph`; taps index with that phase.
         const int chunks_per_row = pitch / 16;
         const uint8_t* frame_end = frames + (size_t)n_frames * H * W * 3;
-        const int n_chunks = srows * chunks_per_row;
-        // four 16-byte loads in flight per thread before the first shared-memory store: the copy
-        // is latency-bound otherwise (one DRAM round trip per loop iteration)
-        for (int t0 = threadIdx.x; t0 < n_chunks; t0 += 4 * kThreads) {
-            uint4 v[4];
-            int off[4];
+        // One warp per staged row, lanes over its 16-byte chunks: the row's base pointer, its alignment and the bounds test
+        // are computed once per row and warp (the flat chunk loop of round 1 spent ~40 instructions per chunk on a division,
+        // two table reads and 64-bit address arithmetic: 45 % of the kernel's instructions, profiles/r02_crop_ncu.md).
+        // Two rows' loads (up to six 16-byte loads per lane) are in flight per warp before the first shared-memory store.
+        const int lane_s = threadIdx.x & 31, wrp_s = threadIdx.x >> 5;
+        constexpr int kWarpsC = kThreads / 32;
+        for (int rb = wrp_s; rb < srows; rb += 2 * kWarpsC) {
+            uint4 v[2][3];
+            bool on[2];
+            int nch[2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int t = t0 + u * kThreads;
-                v[u] = make_uint4(0, 0, 0, 0);
-                off[u] = -1;
-                if (t >= n_chunks) continue;
-                const int r = t / chunks_per_row, c = t - r * chunks_per_row;
+            for (int u = 0; u < 2; ++u) {
+                const int r = rb + u * kWarpsC;
+                on[u] = r < srows;
+                nch[u] = 0;
+                if (!on[u]) continue;
                 const uint8_t* g0 = src + ((size_t)(slots ? s_srow[r] : by0 + r) * W + bx0) * 3;
-                const uint8_t* ga = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(g0) & ~uintptr_t(15)) + 16 * c;
-                off[u] = r * pitch + 16 * c;
-                if (ga >= frames && ga + 16 <= frame_end) {
-                    v[u] = __ldg(reinterpret_cast<const uint4*>(ga));
-                } else {                                    // first/last bytes of the allocation
-                    uint8_t* vb = reinterpret_cast<uint8_t*>(&v[u]);
-                    for (int k = 0; k < 16; ++k)
-                        if (ga + k >= frames && ga + k < frame_end) vb[k] = __ldg(ga + k);
+                const uint8_t* ga = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(g0) & ~uintptr_t(15));
+                const bool inside = ga >= frames && ga + (size_t)16 * chunks_per_row <= frame_end;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int c = lane_s + 32 * k;
+                    v[u][k] = make_uint4(0, 0, 0, 0);
+                    if (c >= chunks_per_row) continue;
+                    nch[u] = k + 1;
+                    if (inside) {
+                        v[u][k] = __ldg(reinterpret_cast<const uint4*>(ga) + c);
+                    } else {                                    // first / last bytes of the allocation
+                        uint8_t* vb = reinterpret_cast<uint8_t*>(&v[u][k]);
+                        for (int b = 0; b < 16; ++b)
+                            if (ga + 16 * c + b >= frames && ga + 16 * c + b < frame_end) vb[b] = __ldg(ga + 16 * c + b);
+                    }
+                }
+                // (rows wider than 96 chunks = 1536 bytes: the remaining chunks one at a time)
+                for (int c = lane_s + 96; c < chunks_per_row; c += 32) {
+                    uint4 q = make_uint4(0, 0, 0, 0);
+                    if (inside) q = __ldg(reinterpret_cast<const uint4*>(ga) + c);
+                    else {
+                        uint8_t* vb = reinterpret_cast<uint8_t*>(&q);
+                        for (int b = 0; b < 16; ++b)
+                            if (ga + 16 * c + b >= frames && ga + 16 * c + b < frame_end) vb[b] = __ldg(ga + 16 * c + b);
+                    }
+                    *reinterpret_cast<uint4*>(smem + r * pitch + 16 * c) = q;
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (off[u] >= 0) *reinterpret_cast<uint4*>(smem + off[u]) = v[u];
+            for (int u = 0; u < 2; ++u) {
+                if (!on[u]) continue;
+                const int r = rb + u * kWarpsC;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (k < nch[u]) *reinterpret_cast<uint4*>(smem + r * pitch + 16 * (lane_s + 32 * k)) = v[u][k];
+            }
         }
         __syncthreads();
     }
@@ -400,7 +438,7 @@ int k_crop_warp(hbp_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w,
         HBP_CUDA(cudaFuncSetAttribute(crop_warp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2 * kSmemPad));
         ctx->attr_flags |= ATTR_CROP;
     }
-    dim3 grid((out_h + kBandRows - 1) / kBandRows, P);
+    dim3 grid((out_h + kBandRows - 1) / kBandRows, P);      // (kBandRows output rows per CTA)
     if (out_dtype == HBP_F16)
         crop_warp_kernel<__half><<<grid, kThreads, kSmemBudget + 2 * kSmemPad, ctx->stream>>>(
             frames, n_frames, h, w, M, frame_idx, P, out_h, out_w, swap_rb, (__half*)out, live);
