@@ -30,7 +30,7 @@ namespace {
 constexpr int kBandRows = 32;             // output rows per CTA: the per-CTA tables (column deltas, tap offsets, x weights) are built once per band
 constexpr int kPassRows = 8;              // ... and the band is sampled in passes of <= 8 rows whose source rows fit the shared-memory budget
 constexpr int kThreads = 256;
-constexpr int kSmemBudget = 28 * 1024;    // per CTA: 7 CTAs of 256 threads per SM
+constexpr int kSmemBudget = 56 * 1024;    // per CTA: three CTAs of 256 threads per SM (80 registers per thread decide that, not this)
 constexpr int kSmemPad = 16;              // bytes in front of / behind the staged box: a zero-weight tap may read up to 3 bytes outside it
 constexpr int kMaxTabW = 512;             // output widths up to this use the per-CTA column tables
 
@@ -81,7 +81,7 @@ template <> __device__ __forceinline__ __half finish_acc<__half>(unsigned bits) 
 }
 
 template <typename OutT>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 3)
 crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
                  const double* __restrict__ Ms, const int* __restrict__ frame_idx, int P,
                  int out_h, int out_w, int swap_rb, OutT* __restrict__ out, const int* __restrict__ live) {
@@ -110,7 +110,7 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
     if (tab)
         for (int x = threadIdx.x; x < out_w; x += kThreads) {
             s_ad[x] = __double2int_rn(__dmul_rn(__dmul_rn(A.m00, (double)x), 1024.0));
-            s_bd[x] = __double2int_rn(__dmul_rn(__dmul_rn(A.m10, (double)x), 1024.0));
+            s_bd[x] = axis ? 0 : __double2int_rn(__dmul_rn(__dmul_rn(A.m10, (double)x), 1024.0));      // (rint(0 * x * 1024) = 0)
         }
     int f = frame_idx[p];
     f = f < 0 ? 0 : (f >= n_frames ? n_frames - 1 : f);
@@ -143,6 +143,155 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
         const int srows = axis ? min(nrows, 2 * nr) : nrows;
         *need = (cols > 0 && nrows > 0) ? (long long)srows * (((long long)cols * 3 + 15 + 15) / 16 * 16) : 0;
     };
+    const size_t plane = (size_t)out_h * out_w;
+    OutT* __restrict__ obase = out + (size_t)p * 3 * plane;
+    __shared__ int s_xr[2];
+    if (axis) {
+        // axis-aligned: the source column range is the same for every output row -- two coordinate evaluations
+        if (threadIdx.x == 0) {
+            int Xa, Xb, Yd;
+            src_coord(A, 0, row0, Xa, Yd);
+            src_coord(A, out_w - 1, row0, Xb, Yd);
+            int xmin = min(Xa >> 5, Xb >> 5), xmax = max(Xa >> 5, Xb >> 5) + 1;
+            xmin = max(xmin, 0); xmax = min(xmax, W - 1);
+            s_xr[0] = xmin; s_xr[1] = xmax - xmin + 1;
+        }
+        __syncthreads();
+    // ---- row mode (every axis-aligned map whose source rows are <= 1536 bytes wide: all crop_and_resize / resize boxes up
+    // to ~500 source pixels): after the per-band tables NO block barrier is left.  Every warp owns output rows ry = warp,
+    // warp + 8, ...: it stages the two source rows the row taps in its private shared-memory slice (16-byte coalesced loads,
+    // the next row's loads already in flight while the current row is sampled), samples its 2 x 3 pixels per lane with the
+    // integer blend below, and moves on.  Same arithmetic as the band path, different schedule.
+    {
+        const int bx0 = s_xr[0], bcols = s_xr[1];
+        const int pitch = ((bcols * 3 + 15 + 15) / 16) * 16;
+        const int chunks_per_row = pitch / 16;
+        constexpr int kWarpsC = kThreads / 32;
+        if (bcols > 0 && kWarpsC * 2 * (pitch + 16) <= kSmemBudget + kSmemPad && (out_w & 1) == 0) {
+            const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+            {
+                const int X0c = __double2int_rn(__dmul_rn(A.m02, 1024.0)) + 16;
+                for (int x = threadIdx.x; x < ((out_w + 7) & ~7); x += kThreads) {
+                    const int X = (X0c + s_ad[min(x, out_w - 1)]) >> 5;
+                    const int sx = X >> 5, fx = X & 31;
+                    const unsigned wx0 = (unsigned)sx < (unsigned)W ? 32u - fx : 0u, wx1 = (unsigned)(sx + 1) < (unsigned)W ? (unsigned)fx : 0u;
+                    s_cx3[x] = (min(max(sx, bx0 - 1), bx0 + bcols - 1) - bx0) * 3;
+                    s_wx[x] = wx0 | (wx1 << 16);
+                }
+            }
+            __syncthreads();
+            uint8_t* const wbuf = smem_all + wrp * 2 * (pitch + 16);        // [tap row][16-byte front pad | pitch]
+            const uint8_t* frame_end = frames + (size_t)n_frames * H * W * 3;
+            const int src_lo = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+            const bool pair_ok = (plane & 1) == 0 && (reinterpret_cast<uintptr_t>(obase) & (2 * sizeof(OutT) - 1)) == 0;
+            uint4 v[2][3];
+            int srow[2] = {0, 0};
+            auto request = [&](int ry) {            // global loads of the two source rows of output row row0 + ry -> registers
+                const int y = row0 + ry;
+                const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(A.m11, (double)y), A.m12), 1024.0)) + 16;
+                const int sy = (Y0 >> 5) >> 5;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int r = min(max(sy + t, 0), H - 1);       // (a tap outside the frame has weight 0: any valid row will do)
+                    srow[t] = r;
+                    const uint8_t* g0 = src + ((size_t)r * W + bx0) * 3;
+                    const uint8_t* ga = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(g0) & ~uintptr_t(15));
+                    const bool inside = ga >= frames && ga + (size_t)16 * chunks_per_row <= frame_end;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int c = lane + 32 * k;
+                        v[t][k] = make_uint4(0, 0, 0, 0);
+                        if (c >= chunks_per_row) continue;
+                        if (inside) {
+                            v[t][k] = __ldg(reinterpret_cast<const uint4*>(ga) + c);
+                        } else {                                    // first / last bytes of the allocation
+                            uint8_t* vb = reinterpret_cast<uint8_t*>(&v[t][k]);
+                            for (int b = 0; b < 16; ++b)
+                                if (ga + 16 * c + b >= frames && ga + 16 * c + b < frame_end) vb[b] = __ldg(ga + 16 * c + b);
+                        }
+                    }
+                }
+            };
+            if (wrp < rows) request(wrp);
+            for (int ry = wrp; ry < rows; ry += kWarpsC) {
+                const int y = row0 + ry;
+                const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(A.m11, (double)y), A.m12), 1024.0)) + 16;
+                const int Y = Y0 >> 5, sy = Y >> 5, fy = Y & 31;
+                const unsigned wy0 = (unsigned)sy < (unsigned)H ? 32u - fy : 0u, wy1 = (unsigned)(sy + 1) < (unsigned)H ? (unsigned)fy : 0u;
+                const int base0 = 16 + ((src_lo + (srow[0] * W + bx0) * 3) & 15);
+                const int base1 = (pitch + 16) + 16 + ((src_lo + (srow[1] * W + bx0) * 3) & 15);
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (lane + 32 * k < chunks_per_row) *reinterpret_cast<uint4*>(wbuf + t * (pitch + 16) + 16 + 16 * (lane + 32 * k)) = v[t][k];
+                if (chunks_per_row > 96) {
+                    // rows wider than 1536 bytes (source boxes beyond ~500 pixels): the rest of the row, not prefetched
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const uint8_t* g0 = src + ((size_t)srow[t] * W + bx0) * 3;
+                        const uint8_t* ga = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(g0) & ~uintptr_t(15));
+                        const bool inside = ga >= frames && ga + (size_t)16 * chunks_per_row <= frame_end;
+                        for (int c = lane + 96; c < chunks_per_row; c += 32) {
+                            uint4 q = make_uint4(0, 0, 0, 0);
+                            if (inside) q = __ldg(reinterpret_cast<const uint4*>(ga) + c);
+                            else {
+                                uint8_t* vb = reinterpret_cast<uint8_t*>(&q);
+                                for (int b = 0; b < 16; ++b)
+                                    if (ga + 16 * c + b >= frames && ga + 16 * c + b < frame_end) vb[b] = __ldg(ga + 16 * c + b);
+                            }
+                            *reinterpret_cast<uint4*>(wbuf + t * (pitch + 16) + 16 + 16 * c) = q;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (ry + kWarpsC < rows) request(ry + kWarpsC);       // next row's loads fly while this one is sampled
+                OutT* orow0 = obase + (size_t)y * out_w + (swap_rb ? 2 * plane : 0);
+                OutT* orow1 = obase + (size_t)y * out_w + plane;
+                OutT* orow2 = obase + (size_t)y * out_w + (swap_rb ? 0 : 2 * plane);
+                for (int x0 = 2 * lane; x0 < out_w; x0 += 64) {
+                    const int2 c3 = *reinterpret_cast<const int2*>(&s_cx3[x0]);
+                    const uint2 wx = *reinterpret_cast<const uint2*>(&s_wx[x0]);
+                    OutT r[3][2];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int cc = k ? c3.y : c3.x;
+                        const unsigned wxx = k ? wx.y : wx.x;
+                        const unsigned wr0 = wxx * wy0, wr1 = wxx * wy1;
+                        unsigned acc0 = 0x4B000000u, acc1 = 0x4B000000u, acc2 = 0x4B000000u;
+                        auto row = [&](int b, unsigned wr) {
+                            const uint32_t* wp = reinterpret_cast<const uint32_t*>(wbuf + (b & ~3));
+                            const uint32_t lo = wp[0], mid = wp[1], hi = wp[2];
+                            const unsigned sh = (unsigned)b << 3;                  // funnel shift takes the amount mod 32
+                            const uint32_t v0 = __funnelshift_r(lo, mid, sh), v1 = __funnelshift_r(mid, hi, sh);
+                            acc0 = __dp2a_lo(wr, __byte_perm(v0, v1, 0x4430), acc0);
+                            acc1 = __dp2a_lo(wr, __byte_perm(v0, v1, 0x4441), acc1);
+                            acc2 = __dp2a_lo(wr, __byte_perm(v0, v1, 0x4452), acc2);
+                        };
+                        row(base0 + cc, wr0);
+                        row(base1 + cc, wr1);
+                        r[0][k] = finish_acc<OutT>(acc0);
+                        r[1][k] = finish_acc<OutT>(acc1);
+                        r[2][k] = finish_acc<OutT>(acc2);
+                    }
+                    OutT* const op[3] = {orow0 + x0, orow1 + x0, orow2 + x0};
+                    if (pair_ok) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            if (sizeof(OutT) == 2) *reinterpret_cast<uint32_t*>(op[c]) = *reinterpret_cast<const uint32_t*>(r[c]);
+                            else *reinterpret_cast<uint2*>(op[c]) = *reinterpret_cast<const uint2*>(r[c]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { op[c][0] = r[c][0]; op[c][1] = r[c][1]; }
+                    }
+                }
+                __syncwarp();                   // the slice is restaged for this warp's next row
+            }
+            return;
+        }
+    }
+    }
     // (all box arithmetic is double precision, slow on this part: spread it over threads instead of leaving 255 threads
     // at a barrier behind thread 0 -- the round-1 profile had stall_barrier on top)
     __shared__ int s_fit[4];
@@ -171,8 +320,6 @@ crop_warp_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
     }
     __syncthreads();
     const int groups = (out_w + 7) / 8;                 // 8 output pixels per thread-iteration
-    const size_t plane = (size_t)out_h * out_w;
-    OutT* __restrict__ obase = out + (size_t)p * 3 * plane;
     bool tables_built = false;
     for (int pr0 = row0; pr0 < row0 + rows; pr0 += rp) {
     const int prow = min(rp, row0 + rows - pr0);
