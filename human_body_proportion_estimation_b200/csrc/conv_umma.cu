@@ -2173,6 +2173,7 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
 }
 
 struct UmmaGroup {
+    UmmaGroup* next = nullptr;       // tables of the same launch for other batch sizes (a captured graph keeps pointing at its own)
     GroupEntry* d_table = nullptr;
     std::vector<GroupEntry> h;
     GroupHeader hdr;
@@ -2183,20 +2184,27 @@ struct UmmaGroup {
 };
 
 void umma_group_destroy(UmmaGroup* g) {
-    if (!g) return;
-    if (g->d_table) cudaFree(g->d_table);
-    delete g;
+    while (g) {
+        UmmaGroup* nx = g->next;
+        if (g->d_table) cudaFree(g->d_table);
+        delete g;
+        g = nx;
+    }
 }
 
 // one persistent launch over the work items of `members` (mode-0 plans in m.umma); `slot_index` keys the table
 static int group_launch(hbp_ctx* ctx, HrnetModel& m, int slot_index, const int* members, int n, int P, cudaStream_t st) {
     if (n < 1 || n > kMaxGroup) { hbp_set_error("group of %d convolutions (max %d)", n, kMaxGroup); return HBP_ERR_INVALID; }
     if ((int)m.groups.size() < (int)m.ops.size()) m.groups.resize(m.ops.size(), nullptr);
-    UmmaGroup*& g = m.groups[slot_index];
+    // one table per batch size: the graphs of other batch sizes keep replaying with theirs
+    UmmaGroup* g = m.groups[slot_index];
+    while (g && !(g->P == P && g->tl == (const void*)m.d_timeline)) g = g->next;
     if (!g) {
         g = new UmmaGroup();
         g->h.resize(n);
         HBP_CUDA(cudaMalloc(&g->d_table, sizeof(GroupEntry) * n));
+        g->next = m.groups[slot_index];
+        m.groups[slot_index] = g;
     }
     if (g->P != P || g->tl != (const void*)m.d_timeline) {
         // (re)build the table for this batch size.  Never inside a graph capture: the first forward of a
@@ -2363,6 +2371,7 @@ int umma_launch(hbp_ctx* ctx, HrnetModel& m, int op_index, UmmaPlan* pl, int P, 
 // chain launch (conv_umma_chain_kernel): host side
 // ---------------------------------------------------------------------------
 struct UmmaChain {
+    UmmaChain* next = nullptr;           // per batch size, like UmmaGroup
     ChainEntry* d_table = nullptr;
     unsigned* d_flags = nullptr;         // [n_layers][n_tiles] + 2 words of launch state
     std::vector<ChainEntry> h;
@@ -2376,10 +2385,14 @@ struct UmmaChain {
 };
 
 void umma_chain_destroy(UmmaChain* c) {
-    if (!c) return;
-    if (c->d_table) cudaFree(c->d_table);
-    if (c->d_flags) cudaFree(c->d_flags);
-    delete c;
+    while (c) {
+        UmmaChain* nx = c->next;
+        if (c->d_table) cudaFree(c->d_table);
+        if (c->d_flags) cudaFree(c->d_flags);
+        if (c->hdr.trace) cudaFree(c->hdr.trace);
+        delete c;
+        c = nx;
+    }
 }
 
 static int encode_act_map(EncodeTiledFn enc, CUtensorMap* tm, const HrnetModel& m, const HTensor& t, int capP, int c_box, int w_box,
@@ -2402,8 +2415,14 @@ int umma_chain_launch(hbp_ctx* ctx, HrnetModel& m, int chain_index, int P, cudaS
     const int L = (int)cop.members.size();
     if (!enabled || L < 2 || L > kMaxChain) return 1;
     if ((int)m.chains.size() < (int)m.ops.size()) m.chains.resize(m.ops.size(), nullptr);
-    UmmaChain*& c = m.chains[chain_index];
-    if (!c) c = new UmmaChain();
+    UmmaChain* c = m.chains[chain_index];
+    while (c && !c->unsupported && !(c->P == P && c->tl == (const void*)m.d_timeline)) c = c->next;
+    if (!c) {
+        c = new UmmaChain();
+        c->hdr.trace = nullptr;
+        c->next = m.chains[chain_index];
+        m.chains[chain_index] = c;
+    }
     if (c->unsupported) return 1;
     if (c->P != P || c->tl != (const void*)m.d_timeline) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;

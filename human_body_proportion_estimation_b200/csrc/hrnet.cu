@@ -805,7 +805,8 @@ void hrnet_dims(hbp_ctx* ctx, int* h, int* w, int* width) {
 
 static void free_batch_state(hbp_ctx* ctx, HrnetModel* m) {
     cudaStreamSynchronize(ctx->stream);
-    if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+    for (HrnetModel::HGraph& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    m->graphs.clear();
     for (UmmaPlan* p : m->umma) if (p) umma_plan_destroy(p);
     m->umma.clear();
     for (UmmaGroup* g : m->groups) if (g) umma_group_destroy(g);
@@ -1110,42 +1111,55 @@ int hrnet_forward(hbp_ctx* ctx, const __half* crops, int P, void* heatmaps, int 
         HBP_CUDA(cudaStreamSynchronize(ctx->stream));
         m->timeline_pending = true;
     }
-    const bool same_key = m->graph_exec && m->graph_P == P && m->graph_dtype == out_dtype &&
-                          m->graph_in == (const void*)crops && m->graph_out == heatmaps &&
-                          m->graph_engine == m->engine;
     static const bool no_graph = getenv("HBP_NO_GRAPH") != nullptr;
-    if (same_key && !no_graph) {
-        HBP_CUDA(cudaGraphLaunch(m->graph_exec, ctx->stream));
-        ctx->launches += m->graph_nodes;
+    m->graph_P = P;
+    uint64_t n = 0;
+    if (no_graph) {
+        s = issue_ops(ctx, m, crops, P, heatmaps, out_dtype, &n);
+        if (s) return s;
+        ctx->launches += n;
         return HBP_OK;
     }
-    const bool seen_before = m->graph_P == P && m->graph_dtype == out_dtype && m->graph_in == (const void*)crops &&
-                             m->graph_out == heatmaps && m->graph_engine == m->engine;
-    uint64_t n = 0;
-    if (seen_before && !no_graph) {
-        // second consecutive call with the same key: capture it (plans already exist, so no
-        // allocation or tensor-map encoding happens inside the capture)
-        if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+    HrnetModel::HGraph* slot = nullptr;
+    for (HrnetModel::HGraph& g : m->graphs)
+        if (g.P == P && g.dtype == out_dtype && g.in == (const void*)crops && g.out == heatmaps && g.engine == m->engine) { slot = &g; break; }
+    if (slot && slot->exec) {
+        slot->stamp = ++m->graph_clock;
+        HBP_CUDA(cudaGraphLaunch(slot->exec, ctx->stream));
+        ctx->launches += slot->nodes;
+        return HBP_OK;
+    }
+    if (slot) {
+        // second call with this key: capture it (plans and group tables exist since the eager first call, so nothing is
+        // allocated or encoded inside the capture)
         cudaGraph_t g = nullptr;
         HBP_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         s = issue_ops(ctx, m, crops, P, heatmaps, out_dtype, &n);
         cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
         if (s) { if (g) cudaGraphDestroy(g); return s; }
         if (e != cudaSuccess) return hbp_cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
-        e = cudaGraphInstantiate(&m->graph_exec, g, 0);
+        e = cudaGraphInstantiate(&slot->exec, g, 0);
         cudaGraphDestroy(g);
-        if (e != cudaSuccess) { m->graph_exec = nullptr; return hbp_cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
-        m->graph_nodes = n;
-        HBP_CUDA(cudaGraphLaunch(m->graph_exec, ctx->stream));
+        if (e != cudaSuccess) { slot->exec = nullptr; return hbp_cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+        slot->nodes = n;
+        slot->stamp = ++m->graph_clock;
+        HBP_CUDA(cudaGraphLaunch(slot->exec, ctx->stream));
         ctx->launches += n;
         return HBP_OK;
     }
-    if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+    // first call with this key: eager (creates the plans), and remember the key
     s = issue_ops(ctx, m, crops, P, heatmaps, out_dtype, &n);
     if (s) return s;
     ctx->launches += n;
-    m->graph_P = P; m->graph_dtype = out_dtype; m->graph_in = crops; m->graph_out = heatmaps;
-    m->graph_engine = m->engine;
+    if ((int)m->graphs.size() >= HrnetModel::kMaxGraphs) {
+        size_t lru = 0;
+        for (size_t i = 1; i < m->graphs.size(); ++i) if (m->graphs[i].stamp < m->graphs[lru].stamp) lru = i;
+        if (m->graphs[lru].exec) { HBP_CUDA(cudaStreamSynchronize(ctx->stream)); cudaGraphExecDestroy(m->graphs[lru].exec); }
+        m->graphs.erase(m->graphs.begin() + lru);
+    }
+    HrnetModel::HGraph g;
+    g.P = P; g.dtype = out_dtype; g.engine = m->engine; g.in = crops; g.out = heatmaps; g.stamp = ++m->graph_clock;
+    m->graphs.push_back(g);
     return HBP_OK;
 }
 
@@ -1166,7 +1180,6 @@ int hrnet_forward_until(hbp_ctx* ctx, const __half* crops, int P, int stop_after
     HBP_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < kStreams - 1; ++i) if (m->side[i]) HBP_CUDA(cudaStreamSynchronize(m->side[i]));
     m->graph_P = P;          // hrnet_debug_tensor sizes its copy by the batch of the last forward
-    m->graph_in = nullptr;   // (never equal to a caller pointer: the next hbp_hrnet_forward runs eagerly once, then re-captures)
     return HBP_OK;
 }
 

@@ -63,11 +63,19 @@ struct HrnetModel {
     std::vector<UmmaPlan*> umma;                // one per op (nullptr = SIMT)
     std::vector<UmmaGroup*> groups;             // one per op (OP_GROUP ops only)
     std::vector<UmmaChain*> chains;             // one per op (OP_CHAIN ops only)
-    cudaGraphExec_t graph_exec = nullptr;
-    int graph_P = 0, graph_dtype = -1, graph_engine = -1;
-    const void* graph_in = nullptr;
-    void* graph_out = nullptr;
-    uint64_t graph_nodes = 0;
+    // CUDA graphs of the forward, keyed by (batch, input / output pointers, heatmap dtype, engine): a stream of frames
+    // with a different person count each keeps one graph per count (least recently used of kMaxGraphs is dropped)
+    struct HGraph {
+        int P = 0, dtype = -1, engine = -1;
+        const void* in = nullptr;
+        void* out = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        uint64_t nodes = 0, stamp = 0;
+    };
+    static constexpr int kMaxGraphs = 16;
+    std::vector<HGraph> graphs;
+    uint64_t graph_clock = 0;
+    int graph_P = 0;                            // batch of the last forward (hrnet_debug_tensor sizes its copy by it)
     cudaStream_t side[7] = {};                  // streams 1.. (stream 0 is the context's): one per resolution branch
     cudaEvent_t ev_fork = nullptr, ev_join[7] = {};
     std::vector<cudaEvent_t> ev_pool;

@@ -116,3 +116,20 @@ def test_hrnet_w32_per_stage_error_table(eng):
     for key, e_max, _ in rows:
         assert e_max - prev < 4e-3, (key, e_max, prev)
         prev = max(prev, e_max)
+
+
+def test_graph_cache_alternating_batch_sizes(eng):
+    """a stream whose person count changes every frame keeps one CUDA graph per batch size (and one group table
+    per batch size behind it): replays stay bit-identical to the eager first pass when the sizes alternate."""
+    eng.load_hrnet(None, 32, 256, 192, seed=0)
+    crops = np.random.default_rng(21).uniform(0, 1, (16, 3, 256, 192)).astype(np.float16)
+    big = eng.hrnet_forward(crops)                      # capacity 16 from the start: the plans do not change below
+    first = {}
+    for n in (5, 8, 3, 16):
+        first[n] = eng.hrnet_forward(crops[:n])          # eager
+        assert np.array_equal(first[n], big[:n])
+    launches0 = eng.kernel_launches()
+    for rep in range(3):                                 # capture on the second visit, replay afterwards
+        for n in (5, 8, 3, 16, 8, 5):
+            assert np.array_equal(eng.hrnet_forward(crops[:n]), first[n]), (rep, n)
+    assert eng.kernel_launches() > launches0
