@@ -112,11 +112,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Watchdog of every in-kernel wait (mbarrier phases, the chain kernel's dependency flags): SM clock cycles after which a
+// wait that has not advanced traps instead of hanging the GPU (a wrong expect_tx byte count or tensor map never
+// completes).  clock64 keeps counting while a context is time-sliced or replayed by a profiler, so the limit is generous
+// (HBP_WATCHDOG_S seconds at ~2 GHz, default 20; 0 disables it) -- set once per process by umma_plan_create.
+__device__ long long g_watchdog_cycles = 40000000000LL;
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     // try_wait suspends the warp in hardware up to the time hint (it wakes on completion), so a
-    // waiting role does not take issue slots from the warps that share its scheduler; a pipeline that has not
-    // advanced for ~2 s is a bug (wrong expect_tx byte count, bad tensor map):
-    // trap instead of hanging the GPU.
+    // waiting role does not take issue slots from the warps that share its scheduler
     long long t0 = 0;
     for (uint32_t spins = 0;; ++spins) {
         uint32_t done;
@@ -130,7 +134,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if ((spins & 1023u) == 1023u) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000LL) __trap();
+            else if (g_watchdog_cycles > 0 && now - t0 > g_watchdog_cycles) __trap();
         }
     }
 }
@@ -1379,7 +1383,7 @@ conv_umma_chain_kernel(const ChainEntry* __restrict__ table, const ConvParams p,
         if ((++spins & 4095u) == 0u) {
             const long long now = clock64();
             if (t_start == 0) t_start = now;
-            else if (now - t_start > 8000000000LL) __trap();
+            else if (g_watchdog_cycles > 0 && now - t_start > g_watchdog_cycles) __trap();
         }
     };
 
@@ -2036,6 +2040,11 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     EncodeTiledFn enc = get_encode();
     if (!enc) { delete pl; hbp_set_error("cuTensorMapEncodeTiled unavailable"); return HBP_ERR_CUDA; }
     if (!(ctx->attr_flags & ATTR_UMMA)) {
+        {
+            const char* e = getenv("HBP_WATCHDOG_S");
+            const long long cycles = (long long)((e ? atof(e) : 20.0) * 2.0e9);
+            HBP_CUDA(cudaMemcpyToSymbol(g_watchdog_cycles, &cycles, sizeof(cycles)));
+        }
         HBP_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         HBP_CUDA(cudaFuncSetAttribute(conv_umma_pgroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         HBP_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

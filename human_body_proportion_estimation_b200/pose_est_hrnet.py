@@ -1,7 +1,13 @@
 """`run_demo_pose_est` (human_body_length_est/pose_est_hrnet_trtserver.py:31-146):
-single-person HRNet on whole frames.  Reference preprocessing (:15-19): BGR->RGB,
-/255, cv2.resize to the model size, CHW.  The reference returns None and only
-draws; this returns [(keypts(17,2) image px, conf(17,1)), ...] per frame."""
+single-person HRNet on whole frames.  The reference returns None and only draws; this returns
+[(keypts(17,2) image px, conf(17,1)), ...] per frame.
+
+Documented deviation: the reference's preprocessing (:15-19) divides by 255 FIRST and lets cv2.resize
+interpolate the float64 image, and it resizes only when the model has a fixed input size; here the frame is resized as
+uint8 with cv2.resize's 11-bit fixed point (HBP_PRE_STRETCH, the arithmetic of PoseEstimator.preprocess, which IS
+bit-exact against the reference) and divided by 255 afterwards, always to the model size.  The two differ by the uint8
+rounding of the interpolated value, at most 0.5/255 per pixel -- below the fp16 resolution of the HRNet input for half
+of the value range and two orders of magnitude below the 1e-2 heatmap tolerance; no golden pins this entry point."""
 import numpy as np
 
 from . import engine as _engine

@@ -130,3 +130,38 @@ def test_crop_fp16_finalize_is_exact_for_every_accumulator():
     r = (acc.astype(np.float64) - q.astype(np.float64) * 255.0).astype(np.float32)
     q2 = (q.astype(np.float64) + r.astype(np.float64) * np.float64(np.float32(1.0) / np.float32(255.0))).astype(np.float32)
     assert np.array_equal(q2 * np.float32(2.0 ** -10), ref32)
+
+
+def test_oracle_hrnet_table_matches_library(lib):
+    """the reference arm (bench.py --impl reference) builds its network from oracle/hrnet_table.py and never loads the
+    library under test: both tables, both FLOP counts and both seeded weight sets must be the same"""
+    from human_body_proportion_estimation_b200 import _capi, hrnet_arch
+    from oracle import hrnet_table
+    for width, (h, w) in ((32, (256, 192)), (48, (384, 288))):
+        rows, _, _ = _capi.describe_hrnet(width, h, w)
+        assert [tuple(r[:5]) for r in rows] == hrnet_table.layer_table(width)
+        assert hrnet_table.flops_per_crop(width, h, w) == hrnet_arch.flops_per_crop(width, h, w)[0]
+    wa, wb = hrnet_arch.random_weights(32, 256, 192, 0), hrnet_table.random_weights(32, 0)
+    assert wa.keys() == wb.keys()
+    for k in wa:
+        assert np.array_equal(wa[k][0], wb[k][0]) and np.array_equal(wa[k][1], wb[k][1]), k
+
+
+def test_reference_arm_does_not_load_the_library():
+    """bench.py --impl reference in a fresh interpreter: synthetic inputs, oracle network table, oracle stages -- and no
+    libhbp_b200.so in the process's memory map afterwards"""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import bench\n"
+        "from oracle import hrnet_table, detect, geometry, imgproc, hrnet_fp32\n"
+        "cfg = bench.CONFIGS[2]\n"
+        "frames, dets = bench.synth_inputs(cfg)\n"
+        "w = hrnet_table.random_weights(32, 0)\n"
+        "d = detect.official_nms(dets[0], 0.4, 0.5, classes=[0])[0]\n"
+        "assert d.shape[1] == 6 and 20 <= d.shape[0] <= 48\n"
+        "print('mapped' if any('libhbp' in l for l in open('/proc/self/maps')) else 'clean')\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().endswith("clean")
