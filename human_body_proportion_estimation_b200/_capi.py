@@ -86,6 +86,7 @@ _SIGS = {
                                     _P, _P, _I]),
     "hbp_decode_proportions_affine": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P,
                                            _P, _P, _I]),
+    "hbp_keypoint_lengths": (_I, [_P, _P, _P, _P, _I, _P, _P, _I]),
     "hbp_det_pose_submit": (_I, [_P, C.POINTER(DetPoseParams), _P, _P, _P, _P, _P, _I, _P, C.POINTER(_I)]),
     "hbp_det_pose_collect": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I), _P, _P, _P, _P, _P, _P, _P, _P]),
     "hbp_pose_pipeline": (_I, [_P, C.POINTER(PipelineParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,

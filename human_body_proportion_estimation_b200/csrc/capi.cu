@@ -477,6 +477,25 @@ static int decode_impl(hbp_ctx* ctx, const void* hm, int dtype, int P, int J, in
     return st.finish();
 }
 
+int hbp_keypoint_lengths(hbp_ctx* ctx, const float* kpts_img, const uint32_t* ignored, const double* pixel_to_cm, int P,
+                         float* lengths, double* torso, int mem) {
+    BIND(ctx);
+    HBP_REQUIRE(kpts_img && pixel_to_cm && P >= 0 && (lengths || torso), "bad arguments");
+    if (P == 0) return HBP_OK;
+    Stager st(ctx, mem);
+    const float* dk = st.in(kpts_img, (size_t)P * 34, SC_IN0);
+    const uint32_t* di = st.in(ignored, (size_t)P, SC_IN1);
+    const double* dp = st.in(pixel_to_cm, (size_t)P, SC_IN2);
+    float* o_len = st.out(lengths, (size_t)P * 11, SC_OUT0);
+    double* o_to = st.out(torso, (size_t)P, SC_OUT1);
+    if (st.status) return st.status;
+    int s = k_keypoint_lengths(ctx, dk, di, dp, P, o_len, o_to);
+    if (s) return s;
+    st.back(lengths, o_len, (size_t)P * 11);
+    st.back(torso, o_to, (size_t)P);
+    return st.finish();
+}
+
 int hbp_hrnet_forward(hbp_ctx* ctx, const void* crops, int P, void* heatmaps, int out_dtype, int mem) {
     BIND(ctx);
     HBP_REQUIRE(crops && heatmaps && P > 0, "bad arguments");

@@ -146,6 +146,8 @@ int k_edet_filter(hbp_ctx*, const float* boxes, const float* scores, const float
 int k_crop_warp(hbp_ctx*, const uint8_t* frames, int n_frames, int h, int w, const double* M,
                 const int* frame_idx, int P, int out_h, int out_w, int swap_rb, void* out,
                 int out_dtype, const int* live = nullptr);   // live: optional device count, slots >= *live are skipped
+int k_keypoint_lengths(hbp_ctx*, const float* kpts, const uint32_t* ignored, const double* pixel_to_cm, int P,
+                       float* lengths, double* torso);
 int k_decode_proportions(hbp_ctx*, const void* hm, int dtype, int P, int J, int Hh, int Wh,
                          const float* boxes, const double* height_cm, const float* thr,
                          int quarter, float* kpts_hm, float* kpts_img, float* scores,

@@ -135,6 +135,56 @@ struct SegDef { signed char a, b; };
 __constant__ SegDef kSeg[11] = {{5, 6}, {-2, -1}, {5, 7}, {6, 8}, {9, 7}, {10, 8},
                                 {12, 11}, {12, 14}, {11, 13}, {16, 14}, {15, 13}};
 
+// The 11 segment lengths of one person from its 17 image-space keypoints (lane j holds joint j), called by a full warp
+// (modules/pose_estimator.py:130-200).
+__device__ __forceinline__ void segment_lengths(int lane, float ix, float iy, uint32_t ign_mask, double p2c, int p,
+                                                float* __restrict__ lengths, double* __restrict__ torso) {
+    // chest / crotch: integer midpoints (pose_estimator.py:146-153)
+    const float x5 = __shfl_sync(0xffffffffu, ix, 5), y5 = __shfl_sync(0xffffffffu, iy, 5);
+    const float x6 = __shfl_sync(0xffffffffu, ix, 6), y6 = __shfl_sync(0xffffffffu, iy, 6);
+    const float x11 = __shfl_sync(0xffffffffu, ix, 11), y11 = __shfl_sync(0xffffffffu, iy, 11);
+    const float x12 = __shfl_sync(0xffffffffu, ix, 12), y12 = __shfl_sync(0xffffffffu, iy, 12);
+    const bool have_chest = !((ign_mask >> 5) & 1) && !((ign_mask >> 6) & 1);
+    const bool have_crotch = !((ign_mask >> 11) & 1) && !((ign_mask >> 12) & 1);
+    const SegDef sd = kSeg[lane < 11 ? lane : 0];
+    const float ax = __shfl_sync(0xffffffffu, ix, sd.a < 0 ? 0 : sd.a), ay = __shfl_sync(0xffffffffu, iy, sd.a < 0 ? 0 : sd.a);
+    const float bx = __shfl_sync(0xffffffffu, ix, sd.b < 0 ? 0 : sd.b), by = __shfl_sync(0xffffffffu, iy, sd.b < 0 ? 0 : sd.b);
+    if (lane >= 11) return;
+    float out = 0.f;
+    double out_d = 0.0;
+    if (lane == 1) {
+        if (have_chest && have_crotch) {
+            const long long dx = int_mid(x11, x12) - int_mid(x5, x6);
+            const long long dy = int_mid(y11, y12) - int_mid(y5, y6);
+            const double nrm = sqrt((double)dx * (double)dx + (double)dy * (double)dy);
+            if (nrm > 0.0) { out_d = nrm * p2c; out = (float)out_d; }
+        }
+        if (torso) torso[p] = out_d;
+    } else {
+        const bool vis = !((ign_mask >> sd.a) & 1) && !((ign_mask >> sd.b) & 1);
+        if (vis) {
+            // np.linalg.norm on a float32 2-vector: sqrt(dx*dx + dy*dy), no FMA
+            const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by);
+            const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+            // value * pixel_to_cm with a weak python float -> float32 multiply
+            if (nrm > 0.f) out = __fmul_rn(nrm, (float)p2c);
+        }
+    }
+    if (lengths) lengths[(size_t)p * 11 + lane] = out;
+}
+
+// pose_estimator.py:191-200 on keypoints the caller already holds: one warp per person.
+__global__ void __launch_bounds__(128)
+keypoint_lengths_kernel(const float* __restrict__ kpts, const uint32_t* __restrict__ ignored,
+                        const double* __restrict__ pixel_to_cm, int P, float* __restrict__ lengths,
+                        double* __restrict__ torso) {
+    const int p = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= P) return;
+    const float x = lane < 17 ? kpts[((size_t)p * 17 + lane) * 2] : 0.f;
+    const float y = lane < 17 ? kpts[((size_t)p * 17 + lane) * 2 + 1] : 0.f;
+    segment_lengths(lane, x, y, ignored ? ignored[p] : 0u, pixel_to_cm[p], p, lengths, torso);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 decode_proportions_kernel(const T* __restrict__ hm, int P, int J, int Hh, int Wh,
@@ -217,41 +267,8 @@ decode_proportions_kernel(const T* __restrict__ hm, int P, int J, int Hh, int Wh
     const uint32_t ign_mask = __ballot_sync(0xffffffffu, ign);
     if (lane == 0 && ignored_out) ignored_out[p] = ign_mask;
     if (!(lengths || torso) || J != 17) return;
-
-    // chest / crotch: integer midpoints (pose_estimator.py:146-153)
-    const float x5 = __shfl_sync(0xffffffffu, ix, 5), y5 = __shfl_sync(0xffffffffu, iy, 5);
-    const float x6 = __shfl_sync(0xffffffffu, ix, 6), y6 = __shfl_sync(0xffffffffu, iy, 6);
-    const float x11 = __shfl_sync(0xffffffffu, ix, 11), y11 = __shfl_sync(0xffffffffu, iy, 11);
-    const float x12 = __shfl_sync(0xffffffffu, ix, 12), y12 = __shfl_sync(0xffffffffu, iy, 12);
-    const bool have_chest = !((ign_mask >> 5) & 1) && !((ign_mask >> 6) & 1);
-    const bool have_crotch = !((ign_mask >> 11) & 1) && !((ign_mask >> 12) & 1);
     // :166-168 pixel_to_cm = height_cm / (y2 - y1) in python float (double)
-    const double p2c = height_cm[p] / (double)(y2 - y1);
-    const SegDef sd = kSeg[lane < 11 ? lane : 0];
-    const float ax = __shfl_sync(0xffffffffu, ix, sd.a < 0 ? 0 : sd.a), ay = __shfl_sync(0xffffffffu, iy, sd.a < 0 ? 0 : sd.a);
-    const float bx = __shfl_sync(0xffffffffu, ix, sd.b < 0 ? 0 : sd.b), by = __shfl_sync(0xffffffffu, iy, sd.b < 0 ? 0 : sd.b);
-    if (lane >= 11) return;
-    float out = 0.f;
-    double out_d = 0.0;
-    if (lane == 1) {
-        if (have_chest && have_crotch) {
-            const long long dx = int_mid(x11, x12) - int_mid(x5, x6);
-            const long long dy = int_mid(y11, y12) - int_mid(y5, y6);
-            const double nrm = sqrt((double)dx * (double)dx + (double)dy * (double)dy);
-            if (nrm > 0.0) { out_d = nrm * p2c; out = (float)out_d; }
-        }
-        if (torso) torso[p] = out_d;
-    } else {
-        const bool vis = !((ign_mask >> sd.a) & 1) && !((ign_mask >> sd.b) & 1);
-        if (vis) {
-            // np.linalg.norm on a float32 2-vector: sqrt(dx*dx + dy*dy), no FMA
-            const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by);
-            const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-            // value * pixel_to_cm with a weak python float -> float32 multiply
-            if (nrm > 0.f) out = __fmul_rn(nrm, (float)p2c);
-        }
-    }
-    if (lengths) lengths[(size_t)p * 11 + lane] = out;
+    segment_lengths(lane, ix, iy, ign_mask, height_cm[p] / (double)(y2 - y1), p, lengths, torso);
 }
 
 }  // namespace
@@ -270,6 +287,14 @@ int k_decode_proportions(hbp_ctx* ctx, const void* hm, int dtype, int P, int J, 
         decode_proportions_kernel<__half><<<P, kThreads, 0, ctx->stream>>>(
             (const __half*)hm, P, J, Hh, Wh, boxes, height_cm, thr, quarter, kpts_hm, kpts_img, scores,
             idx, ignored, lengths, torso, live, Maff, crop_h, crop_w);
+    HBP_LAUNCH_CHECK(ctx);
+    return HBP_OK;
+}
+
+int k_keypoint_lengths(hbp_ctx* ctx, const float* kpts, const uint32_t* ignored, const double* pixel_to_cm, int P,
+                       float* lengths, double* torso) {
+    if (P <= 0) return HBP_OK;
+    keypoint_lengths_kernel<<<(P + 3) / 4, 128, 0, ctx->stream>>>(kpts, ignored, pixel_to_cm, P, lengths, torso);
     HBP_LAUNCH_CHECK(ctx);
     return HBP_OK;
 }

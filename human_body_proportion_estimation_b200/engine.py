@@ -286,6 +286,18 @@ class Engine:
             HOST))
         return out
 
+    def keypoint_lengths(self, kpts_img, pixel_to_cm, ignored=None):
+        """Segment lengths from keypoints the caller already holds (reference modules/pose_estimator.py:130-200):
+        kpts_img (P,17,2), pixel_to_cm scalar or (P,), ignored (P,) uint32 bit masks -> lengths_cm (P,11), torso_cm (P,)"""
+        k = _c(kpts_img, np.float32).reshape(-1, 17, 2)
+        P = k.shape[0]
+        p2c = _c(np.broadcast_to(np.asarray(pixel_to_cm, np.float64), (P,)), np.float64)
+        ign = None if ignored is None else _c(ignored, np.uint32).reshape(P)
+        out = dict(lengths_cm=np.zeros((P, 11), np.float32), torso_cm=np.zeros((P,), np.float64))
+        check(self._lib.hbp_keypoint_lengths(self._ctx, ptr(k), ptr(ign), ptr(p2c), P, ptr(out["lengths_cm"]),
+                                             ptr(out["torso_cm"]), HOST))
+        return out
+
     # ---- fused pipeline --------------------------------------------------------
     def pose_pipeline(self, frames, mats, frame_idx, boxes_yxyx_px, height_cm,
                       joint_thr=KEYPOINT_THRES_LIST, swap_rb=True, quarter_offset=False,

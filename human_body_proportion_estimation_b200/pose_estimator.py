@@ -71,26 +71,19 @@ class PoseEstimator:
         return out["kpts_hm"][0], out["scores"][0].reshape(-1, 1).astype(hm.dtype if hm.dtype == np.float32 else np.float32)
 
     @staticmethod
-    def get_keypoint_dist_dict(pixel_to_cm, keypts, ignored_kp_idx=None, strict=False):
-        """Reference :191-200 on ALREADY REMAPPED keypoints.  The fused GPU path is
-        Engine.decode_proportions / pose_pipeline; this host helper exists for callers
-        that hold keypoints only (17x2 values, not a GPU-sized problem) and mirrors the
-        kernel's arithmetic."""
-        k = np.asarray(keypts, np.float32)
-        ign = set(ignored_kp_idx) if ignored_kp_idx is not None else set()
-        have_chest, have_crotch = not ({5, 6} & ign), not ({11, 12} & ign)
-        if strict and not (have_chest and have_crotch):
+    def get_keypoint_dist_dict(pixel_to_cm, keypts, ignored_kp_idx=None, strict=False, engine=None):
+        """Reference :191-200 on ALREADY REMAPPED keypoints: the segment arithmetic of the decode kernel
+        (hbp_keypoint_lengths) on keypoints the caller holds.  strict=True reproduces the reference's UnboundLocalError
+        when a chest/crotch joint is ignored (reference :146-157)."""
+        ign = set(int(j) for j in ignored_kp_idx) if ignored_kp_idx is not None else set()
+        if strict and ({5, 6, 11, 12} & ign):
             raise UnboundLocalError("cannot access local variable 'chest'/'crotch' (reference pose_estimator.py:146-157)")
-        mid = lambda a, b: int(np.float32(a) + np.float32(b)) // 2
-        pts = {j: (None if j in ign else k[j]) for j in range(17)}
-        pts[-1] = [mid(k[5, 0], k[6, 0]), mid(k[5, 1], k[6, 1])] if have_chest else None
-        pts[-2] = [mid(k[11, 0], k[12, 0]), mid(k[11, 1], k[12, 1])] if have_crotch else None
-        seg = ((5, 6), (-2, -1), (5, 7), (6, 8), (9, 7), (10, 8), (12, 11), (12, 14), (11, 13), (16, 14), (15, 13))
+        eng = engine or _engine.default_engine()
+        mask = np.uint32(sum(1 << j for j in ign if 0 <= j < 17))
+        res = eng.keypoint_lengths(np.asarray(keypts, np.float32)[None], float(pixel_to_cm), np.array([mask], np.uint32))
         out = {}
-        for key, (a, b) in zip(_engine.SEGMENT_KEYS, seg):
-            if pts[a] is None or pts[b] is None:
-                v = 0
-            else:
-                v = np.linalg.norm(np.asarray(pts[a]) - np.asarray(pts[b]))
-            out[key] = v * pixel_to_cm if v > 0 else _engine.NOT_VISIBLE
+        for i, key in enumerate(_engine.SEGMENT_KEYS):
+            # chest-crotch is python float in the reference (integer midpoints -> float64 norm)
+            v = res["torso_cm"][0] if i == 1 else res["lengths_cm"][0, i]
+            out[key] = v if v > 0 else _engine.NOT_VISIBLE
         return out

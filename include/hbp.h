@@ -325,6 +325,13 @@ HBP_API int hbp_decode_proportions_affine(hbp_ctx* ctx, const void* heatmaps, in
                            float* scores, int32_t* argmax_idx, uint32_t* ignored,
                            float* lengths_cm, double* torso_cm, int mem);
 
+/* ---- segment lengths from keypoints the caller already holds ------------------- *
+ * modules/pose_estimator.py:130-200 (get_keypoint_dist_dict) without the decode: kpts_img (P,17,2) float32 image px,
+ * ignored (P) bit j = joint j ignored (NULL = none), pixel_to_cm (P) double -> lengths_cm (P,11) float32 in
+ * HBP segment order (0 = not visible), torso_cm (P) double.  Same arithmetic as hbp_decode_proportions. */
+HBP_API int hbp_keypoint_lengths(hbp_ctx* ctx, const float* kpts_img, const uint32_t* ignored,
+                         const double* pixel_to_cm, int P, float* lengths_cm, double* torso_cm, int mem);
+
 #ifdef __cplusplus
 }
 #endif

@@ -271,6 +271,16 @@ def test_pose_estimator_class(eng):
             assert (d[key] == v) if isinstance(v, str) else (float(d[key]) == float(v)), key
     d = PoseEstimator.get_keypoint_dist_dict(0.5, r["xy_img"], {5})
     assert d["shoulder"] == og.NOT_VISIBLE and d["torso"] == og.NOT_VISIBLE
+    # hbp_keypoint_lengths on keypoints alone: every value and type equal to the reference-faithful dict
+    rng = np.random.default_rng(1)
+    for trial in range(8):
+        kk = rng.uniform(-50, 800, (17, 2)).astype(np.float32)
+        for ign in (set(), {0, 9}, {5}, {11, 13}, {16, 14, 7}):
+            a = PoseEstimator.get_keypoint_dist_dict(0.41, kk, ign, engine=eng)
+            b = og.lengths_dict(0.41, kk, ign)
+            assert a == b and all(type(a[k_]) is type(b[k_]) for k_ in a), (trial, ign)
+    batch = eng.keypoint_lengths(np.stack([r["xy_img"]] * 5), np.linspace(0.2, 0.9, 5))
+    assert batch["lengths_cm"].shape == (5, 11) and batch["torso_cm"].shape == (5,)
     with pytest.raises(UnboundLocalError):
         PoseEstimator.get_keypoint_dist_dict(0.5, r["xy_img"], {5}, strict=True)
     eng.load_hrnet(None, 48, 384, 288, seed=1)     # restore the module fixture's model

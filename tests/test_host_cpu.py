@@ -102,15 +102,10 @@ def test_frame_sharding_and_geometry():
     assert d["lankle_lknee"] == "Part not visible"
 
 
-def test_host_length_helper_matches_reference_values():
+def test_length_helper_strict_mode_raises_like_the_reference():
+    """the values themselves come from the GPU (hbp_keypoint_lengths; tests/test_gpu_entrypoints.py)"""
     from human_body_proportion_estimation_b200.pose_estimator import PoseEstimator
-    from oracle import geometry as og
-    rng = np.random.default_rng(1)
-    k = rng.uniform(0, 800, (17, 2)).astype(np.float32)
-    for ign in (set(), {0, 9}, {5}, {11, 13}):
-        a = PoseEstimator.get_keypoint_dist_dict(0.41, k, ign)
-        b = og.lengths_dict(0.41, k, ign)
-        assert a == b
+    k = np.zeros((17, 2), np.float32)
     with pytest.raises(UnboundLocalError):
         PoseEstimator.get_keypoint_dist_dict(0.41, k, {5}, strict=True)
 
