@@ -82,6 +82,9 @@ struct ConvParams {
     int res_mma;                 // halo mode: the residual tile (TMA ring) is added by MMAs against a 32x32 identity instead of the epilogue
     uint32_t c_bytes;            // halo mode: constant operand tiles (ones, identity, bias) between the residual ring and the barriers
     uint32_t idesc32;            // instruction descriptor with N = 32 (residual MMAs)
+    int reverse;                 // halo mode: the CTAs walk the tiles from the last to the first (tile = n_tiles - 1 - index)
+    unsigned long long hint_a, hint_r;   // halo mode: L2 cache policies of the halo / residual TMA loads (kEvictNormal, kEvictFirst)
+    unsigned long long hint_o;           // halo mode: L2 cache policy of the output stores (0 = plain stores)
     int dbg_flags;               // bring-up experiments: 1 = skip the output stores, 2 = skip the bias loads
     long long* dbg;              // optional phase timestamps (8 per CTA, first 64 CTAs), bring-up only
     unsigned long long* tl;      // optional [start, end] globaltimer stamps of this launch (HBP_TIMELINE)
@@ -143,6 +146,37 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// L2 eviction policies in the encoding `createpolicy` produces (what CUTLASS passes as TMA::CacheHintSm90)
+constexpr unsigned long long kEvictNormal = 0x1000000000000000ull, kEvictFirst = 0x12F0000000000000ull, kEvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                                 unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy) : "memory");
+}
+// persistent tile walk of a halo CTA: tile index -> (column tile, row tile, image group) advanced by the grid size without
+// divisions, forwards (tile = blockIdx.x + j * grid) or backwards (tile = n_tiles - 1 - blockIdx.x - j * grid)
+struct TileWalk {
+    int tw, th, tg, dw, dh, dg, tiles_w, tiles_h, rev;
+    __device__ __forceinline__ void init(int first, int step, int tiles_w_, int tiles_h_, int n_tiles, int reverse) {
+        tiles_w = tiles_w_; tiles_h = tiles_h_; rev = reverse;
+        const int per_img = tiles_w * tiles_h;
+        const int tile = reverse ? n_tiles - 1 - first : first;
+        tw = tile % tiles_w; th = (tile / tiles_w) % tiles_h; tg = tile / per_img;
+        dw = step % tiles_w; dh = (step / tiles_w) % tiles_h; dg = step / per_img;
+    }
+    __device__ __forceinline__ void next() {
+        if (!rev) {
+            tw += dw; if (tw >= tiles_w) { tw -= tiles_w; ++th; }
+            th += dh; if (th >= tiles_h) { th -= tiles_h; ++tg; }
+            tg += dg;
+        } else {
+            tw -= dw; if (tw < 0) { tw += tiles_w; --th; }
+            th -= dh; if (th < 0) { th += tiles_h; --tg; }
+            tg -= dg;
+        }
+    }
+};
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -426,7 +460,7 @@ __global__ void __launch_bounds__(kThreads)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ PhaseMaps tmP, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    conv_umma_body(&tmA, &tmB, &tmP.m[0], p, (int)blockIdx.x, (int)blockIdx.y, smem_raw);
+    conv_umma_body(&tmA, &tmB, &tmP.m[0], p, p.reverse ? (int)(gridDim.x - 1u - blockIdx.x) : (int)blockIdx.x, (int)blockIdx.y, smem_raw);
 }
 
 // Persistent grouped launch (mode 0: one TMA box per tap).  A group is a list of independent
@@ -834,33 +868,26 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int T = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
         // halo tile t of this CTA -> ring stage t % a_stages; the stage is free once the MMAs of
         // tile t - a_stages have retired (completion number t / a_stages - 1 of its a_empty barrier)
-        int atw, ath, atg;                       // coordinates of the next tile whose halo is requested
-        {
-            const int tile = (int)blockIdx.x;
-            atw = tile % p.tiles_w; ath = (tile / p.tiles_w) % p.tiles_h; atg = tile / tiles_per_img;
-        }
-        const int astep = (int)gridDim.x;
-        const int adw = astep % p.tiles_w, adh = (astep / p.tiles_w) % p.tiles_h, adg = astep / tiles_per_img;
+        TileWalk aw;                             // coordinates of the next tile whose halo is requested
+        aw.init((int)blockIdx.x, (int)gridDim.x, p.tiles_w, p.tiles_h, p.n_tiles, p.reverse);
         int a_sa = 0, a_lap = 0;
         auto issue_a = [&](int t) {             // called for t = 0, 1, 2, ... in order
             (void)t;
             const int sa = a_sa, lap = a_lap;
-            const int n0 = atg * p.tn, h0 = ath * p.th, w0 = atw * 8;
+            const int n0 = aw.tg * p.tn, h0 = aw.th * p.th, w0 = aw.tw * 8;
             if (lap > 0) mbar_wait(a_empty + 8u * sa, (uint32_t)((lap - 1) & 1));
             if (dbg && lane == 0 && t < 16) dbg[128 + t] = clock64();     // A(t) requested
             if (elect_one()) {
                 for (int cc = 0; cc < p.n_chunks; ++cc) {
                     const uint32_t bar = a_full + 8u * (sa * p.n_chunks + cc);
                     mbar_expect_tx(bar, p.a_box_bytes);
-                    tma_load_4d(a_base + sa * a_tile_bytes + cc * p.a_chunk_bytes, &tmA, bar, cc * p.chunk, w0 - KS / 2, h0 - KS / 2, n0);
+                    tma_load_4d_hint(a_base + sa * a_tile_bytes + cc * p.a_chunk_bytes, &tmA, bar, cc * p.chunk, w0 - KS / 2, h0 - KS / 2, n0, p.hint_a);
                 }
             }
             __syncwarp();
 
             if (++a_sa == p.a_stages) { a_sa = 0; ++a_lap; }
-            atw += adw; if (atw >= p.tiles_w) { atw -= p.tiles_w; ++ath; }
-            ath += adh; if (ath >= p.tiles_h) { ath -= p.tiles_h; ++atg; }
-            atg += adg;
+            aw.next();
         };
         // weights do not depend on the previous launch: request them before the dependency wait
         if (p.b_resident) {
@@ -904,9 +931,8 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // through their own ring so that a slow epilogue never delays the halo requests =====
         if (p.res_smem) {
             const int T = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-            int tw = (int)blockIdx.x % p.tiles_w, th_ = ((int)blockIdx.x / p.tiles_w) % p.tiles_h, tg = (int)blockIdx.x / tiles_per_img;
-            const int step = (int)gridDim.x;
-            const int dw = step % p.tiles_w, dh = (step / p.tiles_w) % p.tiles_h, dg = step / tiles_per_img;
+            TileWalk rw;
+            rw.init((int)blockIdx.x, (int)gridDim.x, p.tiles_w, p.tiles_h, p.n_tiles, p.reverse);
             int sr = 0, lap = 0;
             pdl_wait();
             for (int t = 0; t < T; ++t) {
@@ -914,14 +940,12 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (elect_one()) {
                     mbar_expect_tx(res_full + 8u * sr, (uint32_t)p.r_chunks * p.r_box_bytes);
                     for (int rc = 0; rc < p.r_chunks; ++rc)
-                        tma_load_4d(r_base + sr * r_tile_bytes + rc * p.r_chunk_bytes, &tmR, res_full + 8u * sr, n_off + rc * 64,
-                                    tw * 8, th_ * p.th, tg * p.tn);
+                        tma_load_4d_hint(r_base + sr * r_tile_bytes + rc * p.r_chunk_bytes, &tmR, res_full + 8u * sr, n_off + rc * 64,
+                                         rw.tw * 8, rw.th * p.th, rw.tg * p.tn, p.hint_r);
                 }
                 __syncwarp();
                 if (++sr == p.a_stages) { sr = 0; ++lap; }
-                tw += dw; if (tw >= p.tiles_w) { tw -= p.tiles_w; ++th_; }
-                th_ += dh; if (th_ >= p.tiles_h) { th_ -= p.tiles_h; ++tg; }
-                tg += dg;
+                rw.next();
             }
         }
     } else if (warp <= 2) {
@@ -1088,17 +1112,12 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "r"(a1));
         };
         // tile walk: tile index -> (column tile, row tile, image group), advanced without divisions
-        int tw, th_, tg;
-        {
-            const int tile = (int)blockIdx.x + team * (int)gridDim.x;
-            tw = tile % p.tiles_w; th_ = (tile / p.tiles_w) % p.tiles_h; tg = tile / tiles_per_img;
-        }
-        const int step = teams * (int)gridDim.x;
-        const int dw = step % p.tiles_w, dh = (step / p.tiles_w) % p.tiles_h, dg = step / tiles_per_img;
+        TileWalk ew;
+        ew.init((int)blockIdx.x + team * (int)gridDim.x, teams * (int)gridDim.x, p.tiles_w, p.tiles_h, p.n_tiles, p.reverse);
         bool valid[2];
         size_t obase[2];
         auto locate = [&]() {
-            const int n0 = tg * p.tn, h0 = th_ * p.th, w0 = tw * 8;
+            const int n0 = ew.tg * p.tn, h0 = ew.th * p.th, w0 = ew.tw * 8;
             const size_t origin = (((size_t)n0 * p.Ho + h0) * p.Wo + w0) * p.Cout;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
@@ -1106,11 +1125,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 obase[mt] = origin + row_off[mt];
             }
         };
-        auto advance = [&]() {
-            tw += dw; if (tw >= p.tiles_w) { tw -= p.tiles_w; ++th_; }
-            th_ += dh; if (th_ >= p.tiles_h) { th_ -= p.tiles_h; ++tg; }
-            tg += dg;
-        };
+        auto advance = [&]() { ew.next(); };
         // x = accumulator columns c0..c0+15 -> +bias (+residual q0|q1) -> ReLU -> fp16 -> global
         auto finish16 = [&](const uint32_t* rr, size_t o, int c0, uint4 q0, uint4 q1) {
             float x[16];
@@ -1138,8 +1153,19 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int q = 0; q < 8; ++q) pk[q] = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
             if ((p.dbg_flags & 1) && pk[0].x != __float2half(12345.f)) return;
-            *reinterpret_cast<uint4*>(p.out + o) = *reinterpret_cast<const uint4*>(&pk[0]);
-            *reinterpret_cast<uint4*>(p.out + o + 8) = *reinterpret_cast<const uint4*>(&pk[4]);
+            const uint4 v0 = *reinterpret_cast<const uint4*>(&pk[0]), v1 = *reinterpret_cast<const uint4*>(&pk[4]);
+            if (p.hint_o) {
+                asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p.out + o), "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w), "l"(p.hint_o) : "memory");
+                asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p.out + o + 8), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w), "l"(p.hint_o) : "memory");
+            } else if (p.dbg_flags & 32) {           // bring-up: two 16-byte stores instead of one 32-byte store
+                *reinterpret_cast<uint4*>(p.out + o) = v0;
+                *reinterpret_cast<uint4*>(p.out + o + 8) = v1;
+            } else {
+                // one full 32-byte sector per thread and instruction (STG.256): the rows of a warp's lanes are Cout * 2 bytes
+                // apart, so every 16-byte store was a partial-sector write request of its own
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p.out + o), "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w),
+                             "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w) : "memory");
+            }
         };
 
         pdl_wait();                          // residual reads and output writes follow the previous launch
@@ -1984,6 +2010,13 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     p.idesc32 = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     p.bias_mma = bias_mma ? 1 : 0; p.res_mma = res_mma ? 1 : 0; p.c_bytes = c_bytes;
     p.mode = 1; p.rs = rs; p.a_chunk_bytes = a_chunk_bytes; p.a_box_bytes = a_box_bytes;
+    {
+        static const int l2_hints = env_int("HBP_L2_HINTS", 1), rev_ok = env_int("HBP_REVERSE", 1);
+        p.reverse = (op.reverse && rev_ok) ? 1 : 0;
+        p.hint_a = (op.in_dead && (l2_hints & 1)) ? kEvictFirst : kEvictNormal;
+        p.hint_r = (op.res_dead && (l2_hints & 1)) ? kEvictFirst : kEvictNormal;
+        p.hint_o = (op.out_keep && (l2_hints & 2)) ? kEvictLast : 0ull;
+    }
     p.bias = m.d_bias + op.b_off;
     p.res = op.res >= 0 ? m.bufs[m.tensors[op.res].buf] : nullptr;
     p.out = m.bufs[m.tensors[op.out].buf];
@@ -2037,6 +2070,7 @@ int umma_plan_create(hbp_ctx* ctx, HrnetModel& m, int op_index, int capP, UmmaPl
     UmmaPlan* pl = new UmmaPlan();
     ConvParams& p = pl->prm;
     memset(&p, 0, sizeof(p));
+    p.reverse = (op.reverse && env_int("HBP_REVERSE", 1)) ? 1 : 0;
     EncodeTiledFn enc = get_encode();
     if (!enc) { delete pl; hbp_set_error("cuTensorMapEncodeTiled unavailable"); return HBP_ERR_CUDA; }
     if (!(ctx->attr_flags & ATTR_UMMA)) {

@@ -40,6 +40,10 @@ struct HOp {
     int persist = 0;            // per-tap conv that owns the GPU while it runs: persistent tile walkers (conv_umma_pgroup_kernel)
     int grouped = 0;            // issued by the OP_GROUP / OP_UPADD_GROUP op that lists it in `members`
     std::vector<int> members;   // OP_GROUP / OP_UPADD_GROUP: indices of the member ops
+    // L2 residency (tensors larger than a fraction of the 126 MB L2, i.e. layer1's 256-channel maps): reads of a tensor
+    // whose last reader this op is carry the evict-first policy, and consecutive ops of a chain walk their tiles in
+    // opposite directions so that an op starts on what its producer wrote last (conv_umma.cu: ConvParams::reverse)
+    int reverse = 0, in_dead = 0, res_dead = 0, out_keep = 0;
 };
 
 struct UmmaPlan;                // conv_umma.cu: per-op tensor maps + tile shape (per batch size)
