@@ -154,6 +154,18 @@ __device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy) : "memory");
 }
+// 16 output channels of one pixel = one full 32-byte sector: a single STG.256 when the address allows it (always, for
+// channel counts that are multiples of 16), else two 16-byte stores
+__device__ __forceinline__ void store_half16(__half* dst, const __half2* pk) {
+    const uint4 v0 = *reinterpret_cast<const uint4*>(pk), v1 = *reinterpret_cast<const uint4*>(pk + 4);
+    if ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w),
+                     "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w) : "memory");
+    } else {
+        *reinterpret_cast<uint4*>(dst) = v0;
+        *reinterpret_cast<uint4*>(dst + 8) = v1;
+    }
+}
 // persistent tile walk of a halo CTA: tile index -> (column tile, row tile, image group) advanced by the grid size without
 // divisions, forwards (tile = blockIdx.x + j * grid) or backwards (tile = n_tiles - 1 - blockIdx.x - j * grid)
 struct TileWalk {
@@ -439,8 +451,7 @@ __device__ __forceinline__ void conv_umma_body(const CUtensorMap* tmAp, const CU
                             __align__(16) __half2 pk[8];
 #pragma unroll
                             for (int q = 0; q < 8; ++q) pk[q] = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
-                            *reinterpret_cast<uint4*>(p.out + o) = *reinterpret_cast<const uint4*>(&pk[0]);
-                            *reinterpret_cast<uint4*>(p.out + o + 8) = *reinterpret_cast<const uint4*>(&pk[4]);
+                            store_half16(p.out + o, pk);
                         }
                 }
             }
@@ -725,8 +736,7 @@ conv_umma_pgroup_kernel(const GroupEntry* __restrict__ table, const __grid_const
 #pragma unroll
                                 for (int q = 0; q < 8; ++q) pk[q] = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
                                 if ((dbg & 1) && pk[0].x != __float2half(12345.f)) continue;
-                                *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(&pk[0]);
-                                *reinterpret_cast<uint4*>(out + o + 8) = *reinterpret_cast<const uint4*>(&pk[4]);
+                                store_half16(out + o, pk);
                             }
                     }
                 }
@@ -750,7 +760,7 @@ constexpr int kHaloW = 10;       // 8 output columns + 1 halo column each side
 constexpr int kMaxChunks = 8;
 constexpr int kMaxAStages = 4;   // halo tiles in flight per CTA
 constexpr int kMaxBSlots = 24;   // (3 dx) x 8 Cin chunks: weight slots of three taps each (resident) or ring depth (streamed)
-constexpr int kHaloThreads = 384;   // warp 0 halo + weight TMA, warps 1-2 MMA issuers (warp 1 owns TMEM), warp 3 residual TMA, warps 4-7 / 8-11 two epilogue teams
+constexpr int kHaloThreads = 512;   // warp 0 halo + weight TMA, warps 1-2 MMA issuers (warp 1 owns TMEM), warp 3 residual TMA, warps 4-7 / 8-11 / 12-15 up to three epilogue teams
 constexpr int kMaxAccBufs = 4;
 constexpr uint32_t kHaloBarBytes = 8u * (kMaxAStages * kMaxChunks + 3 * kMaxAStages + 2 * kMaxBSlots + 2 * kMaxAccBufs) + 16u;
 
@@ -1747,8 +1757,7 @@ conv_umma_chain_kernel(const ChainEntry* __restrict__ table, const ConvParams p,
                         __align__(16) __half2 pk[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) pk[u] = __floats2half2_rn(x[2 * u], x[2 * u + 1]);
-                        *reinterpret_cast<uint4*>(o + cc0) = *reinterpret_cast<const uint4*>(&pk[0]);
-                        *reinterpret_cast<uint4*>(o + cc0 + 8) = *reinterpret_cast<const uint4*>(&pk[4]);
+                        store_half16(o + cc0, pk);
                     }
                 }
             }
@@ -1875,7 +1884,7 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     const uint32_t row_bytes = chunk * 2;
     const int tiles_w = (Wo + 7) / 8;
     const int sms = sm_budget;
-    const uint32_t budget = (uint32_t)env_int("HBP_HALO_SMEM_KB", 200) * 1024u;
+    const uint32_t budget = (uint32_t)env_int("HBP_HALO_SMEM_KB", 216) * 1024u;   // (216: layer1's conv3 gets a four-stage halo + residual ring, 52 -> 39 us)
 
     // Candidate tiles: (tn images x th rows, m M-tiles).  One persistent CTA per SM walks
     // ceil(items / SMs) work items of 16*m stacked 8-pixel rows each, so the time of the launch
@@ -2000,7 +2009,10 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     // stage s and accumulator buffer b are always served by the same issuer warp / epilogue team,
     // i.e. the issuer and team counts divide the stage and buffer counts.
     p.teams = (acc_bufs % 2 == 0 && a_stages % 2 == 0) ? 2 : 1;
-    p.issuers = (resident && p.teams == 2 && per_cta > 1) ? env_int("HBP_HALO_ISSUERS", 2) : 1;
+    // a third team (tile j -> team j % 3, accumulator buffer j % 4, ring stage j % a_stages: the barriers count warps, not
+    // teams) for the epilogue-bound shapes: many output columns per tile and few MMAs (layer1's 1x1 convs)
+    if (p.teams == 2 && acc_bufs >= 4 && a_stages >= 4 && per_cta >= 3 && n_tile >= env_int("HBP_HALO_TEAMS3_N", 64)) p.teams = env_int("HBP_HALO_TEAMS", 3);
+    p.issuers = (resident && p.teams >= 2 && per_cta > 1) ? env_int("HBP_HALO_ISSUERS", 2) : 1;
     if (a_stages % p.issuers || acc_bufs % p.issuers) p.issuers = 1;
     p.acc_bufs = acc_bufs; p.a_stages = a_stages; p.b_slots = b_slots; p.b_resident = resident;
     uint32_t cols = 32;
