@@ -1977,7 +1977,7 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     int a_stages = 0, b_slots = 0, resident = 0;
     if (env_int("HBP_HALO_RESIDENT", 1) && fixed + b_all + a_tile <= budget) {
         int fit = (int)((budget - fixed - b_all) / a_tile);
-        if (fit >= std::min(2, want_a)) { resident = 1; a_stages = std::min(fit, want_a); b_slots = k_slots; }
+        if (fit >= std::min(env_int("HBP_HALO_RES_MINA", 2), want_a)) { resident = 1; a_stages = std::min(fit, want_a); b_slots = k_slots; }
     }
     if (!resident) {
         a_stages = std::min(want_a, 2);
