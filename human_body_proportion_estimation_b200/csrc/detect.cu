@@ -117,49 +117,77 @@ yolo_filter_kernel(const float* __restrict__ pred, int N, int nc, float conf_thr
         const int my_row = row00 + 32 * u + lane;
         objs[u] = my_row < N ? __ldg(base + (size_t)my_row * E + 4) : 0.f;
     }
+    // One LANE per flagged row (obj > conf).  A row is 5 + nc floats = up to 12 sectors: the lane first touches every sector
+    // of all its flagged rows (independent loads, one L2 round trip for all of them), then walks the class scores out of
+    // L1 -- walking them cold cost one L2 round trip per sector and row (22 us for a 25200-row head: ncu, r02af).
+    bool flags[kFilterUnroll];
+    float keep_alive = 0.f;
 #pragma unroll
     for (int u = 0; u < kFilterUnroll; ++u) {
-    const int row0 = row00 + 32 * u;
-    const float obj = objs[u];
-    const bool flag = (row0 + lane < N) && (legacy ? (obj >= conf_thres) : (obj > conf_thres));
-    // One LANE per flagged row: its nc class scores are nc independent loads (11 sectors, L1 hits after the first touch of
-    // each), so all flagged rows of the warp are worked on at once -- the warp-cooperative walk (one row after the other,
-    // each a load -> shuffle-reduce -> atomic round trip) cost ~0.85 us per flagged row and warp.
-    if (flag) {
-        const int row = row0 + lane;
-        const float* __restrict__ r = base + (size_t)row * E;
-        const float o = obj;
-        // first-max over classes of (cls*obj) [official] or cls [legacy]; torch.max: NaN propagates as the max, first index on ties
-        float best = -INFINITY;
-        int best_j = 0x7fffffff;
-#pragma unroll 8
-        for (int j = 0; j < nc; ++j) {
-            float c = __ldg(r + 5 + j);
-            if (!legacy) c = __fmul_rn(c, o);
-            if (j == 0) { best = c; best_j = 0; }
-            else if (c > best || (c != c && best == best)) { best = c; best_j = j; }
-        }
-        bool ok = legacy ? true : (best > conf_thres);
-        if (ok && n_classes > 0) {
-            ok = false;
-            for (int k = 0; k < n_classes; ++k) ok |= ((float)best_j == (float)classes[k]);
-        }
-        if (ok) {
-            const int slot = atomicAdd(cand_count + b, 1);
-            if (slot < cap) {
-                const float cx = __ldg(r), cy = __ldg(r + 1), w = __ldg(r + 2), h = __ldg(r + 3);
-                const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
-                Cand c;
-                c.x1 = __fsub_rn(cx, hw); c.y1 = __fsub_rn(cy, hh);
-                c.x2 = __fadd_rn(cx, hw); c.y2 = __fadd_rn(cy, hh);
-                c.conf = legacy ? o : best;
-                c.cls = (float)best_j;
-                c.aux = best;
-                c.src = row;
-                cand[(size_t)b * cap + slot] = c;
-            }
+        const int row = row00 + 32 * u + lane;
+        flags[u] = (row < N) && (legacy ? (objs[u] >= conf_thres) : (objs[u] > conf_thres));
+        if (flags[u]) {
+            const float* __restrict__ r = base + (size_t)row * E;
+            for (int j = 8; j < E; j += 8) keep_alive += __ldg(r + j);
+            keep_alive += __ldg(r + E - 1);
         }
     }
+    float bests[kFilterUnroll];
+    int best_js[kFilterUnroll];
+    unsigned okm[kFilterUnroll];
+    int total = 0;
+#pragma unroll
+    for (int u = 0; u < kFilterUnroll; ++u) {
+        const int row = row00 + 32 * u + lane;
+        const float* __restrict__ r = base + (size_t)row * E;
+        const float o = objs[u];
+        float best = -INFINITY;
+        int best_j = 0x7fffffff;
+        bool ok = false;
+        if (flags[u]) {
+            // first-max over classes of (cls*obj) [official] or cls [legacy]; torch.max: NaN propagates as the max, first index on ties
+#pragma unroll 8
+            for (int j = 0; j < nc; ++j) {
+                float c = __ldg(r + 5 + j);
+                if (!legacy) c = __fmul_rn(c, o);
+                if (j == 0) { best = c; best_j = 0; }
+                else if (c > best || (c != c && best == best)) { best = c; best_j = j; }
+            }
+            if (keep_alive == 1.2345e38f) best = keep_alive;          // (never true: keeps the sector touches above alive)
+            ok = legacy ? true : (best > conf_thres);
+            if (ok && n_classes > 0) {
+                ok = false;
+                for (int k = 0; k < n_classes; ++k) ok |= ((float)best_j == (float)classes[k]);
+            }
+        }
+        bests[u] = best; best_js[u] = best_j;
+        okm[u] = __ballot_sync(0xffffffffu, ok);
+        total += __popc(okm[u]);
+    }
+    // ONE atomic per warp (128 rows): ~800 per-group atomics on the image's single counter serialise at its L2 slice
+    // (~27 cycles each) and were most of the kernel's 22 us
+    if (total == 0) return;
+    int slot0 = 0;
+    if (lane == 0) slot0 = atomicAdd(cand_count + b, total);
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+#pragma unroll
+    for (int u = 0; u < kFilterUnroll; ++u) {
+        const int slot = slot0 + __popc(okm[u] & ((1u << lane) - 1u));
+        slot0 += __popc(okm[u]);
+        if (((okm[u] >> lane) & 1u) && slot < cap) {
+            const int row = row00 + 32 * u + lane;
+            const float* __restrict__ r = base + (size_t)row * E;
+            const float cx = __ldg(r), cy = __ldg(r + 1), w = __ldg(r + 2), h = __ldg(r + 3);
+            const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+            Cand c;
+            c.x1 = __fsub_rn(cx, hw); c.y1 = __fsub_rn(cy, hh);
+            c.x2 = __fadd_rn(cx, hw); c.y2 = __fadd_rn(cy, hh);
+            c.conf = legacy ? objs[u] : bests[u];
+            c.cls = (float)best_js[u];
+            c.aux = bests[u];
+            c.src = row;
+            cand[(size_t)b * cap + slot] = c;
+        }
     }
 }
 
