@@ -690,6 +690,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3])
+    ap.add_argument("--retried", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -703,7 +704,17 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--config", str(args.config)]
         sys.exit(subprocess.call(cmd))
-    run_ours(args, rank, world, local_rank)
+    try:
+        run_ours(args, rank, world, local_rank)
+    except Exception:
+        # a CUDA error is sticky for the process: say what happened and (single GPU, once) measure again in a fresh
+        # process instead of leaving the caller without a line
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        if world > 1 or args.retried:
+            raise
+        os.execv(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + ["--retried"])
 
 
 if __name__ == "__main__":

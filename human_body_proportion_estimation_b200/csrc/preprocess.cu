@@ -93,9 +93,25 @@ __global__ void __launch_bounds__(256)
 resize_kernel(const uint8_t* __restrict__ in, int n, int H, int W, T* __restrict__ out, int out_h,
               int out_w, int ox, int oy, int nw, int nh, double scale_x, double scale_y,
               int identity, int swap_rb, int pad_value, int nchw) {
+    // per CTA, once: the horizontal taps of every content column (byte offsets of the two source pixels and the two
+    // 11-bit coefficients: the double-precision coordinate arithmetic used to run per output pixel) and the 256
+    // possible output values (v / 255 rounded like the reference's float division: three IEEE divisions per pixel
+    // otherwise).  The kernel was instruction-issue bound: 51 % of HBM for 4K -> 640.
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    int4* s_tx = reinterpret_cast<int4*>(s_raw);                         // nw entries: {3*i0, 3*i1, c0, c1}
+    T* s_cvt = reinterpret_cast<T*>(s_raw + (size_t)((nw + 3) & ~3) * sizeof(int4));   // 256 entries
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) s_cvt[v] = cvt<T>(v);
+    if (!identity)
+        for (int x = threadIdx.x; x < nw; x += blockDim.x) {
+            const AxisTap tx = axis_tap(x, scale_x, W, false);
+            s_tx[x] = make_int4(tx.i0 * 3, tx.i1 * 3, tx.c0, tx.c1);
+        }
+    __syncthreads();
     const int groups = (out_w + 3) >> 2;
     const size_t total = (size_t)n * out_h * groups;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const int row_bytes = W * 3;
+    const bool packed = nchw && (out_w & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & (4 * sizeof(T) - 1)) == 0;   // four pixels of a plane row = one aligned store
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
         const int gx = (int)(t % groups);
         const int y = (int)((t / groups) % out_h);
@@ -104,36 +120,78 @@ resize_kernel(const uint8_t* __restrict__ in, int n, int H, int W, T* __restrict
         const bool row_in = y >= oy && y < oy + nh;
         AxisTap ty{0, 0, 0, 0};
         if (row_in && !identity) ty = axis_tap(y - oy, scale_y, H, true);
+        const uint8_t* r0 = src + (size_t)ty.i0 * W * 3;
+        const uint8_t* r1 = src + (size_t)ty.i1 * W * 3;
+        int vv[4][3];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int x = gx * 4 + k;
-            if (x >= out_w) break;
-            int v[3] = {pad_value, pad_value, pad_value};
-            if (row_in && x >= ox && x < ox + nw) {
+            vv[k][0] = vv[k][1] = vv[k][2] = pad_value;
+            if (x < out_w && row_in && x >= ox && x < ox + nw) {
                 if (identity) {
                     const uint8_t* q = src + ((size_t)(y - oy) * W + (x - ox)) * 3;
-                    v[0] = __ldg(q); v[1] = __ldg(q + 1); v[2] = __ldg(q + 2);
+                    vv[k][0] = __ldg(q); vv[k][1] = __ldg(q + 1); vv[k][2] = __ldg(q + 2);
                 } else {
-                    const AxisTap tx = axis_tap(x - ox, scale_x, W, false);
-                    const uint8_t* r0 = src + (size_t)ty.i0 * W * 3;
-                    const uint8_t* r1 = src + (size_t)ty.i1 * W * 3;
+                    const int4 tx = s_tx[x - ox];
+                    if (tx.x + 12 <= row_bytes) {
+                        // the two taps are six consecutive bytes: three aligned 32-bit loads per source row and two funnel
+                        // shifts instead of twelve byte loads (the kernel was bound by L1 requests, not by DRAM bytes);
+                        // the loads stay inside the row, the last two columns of a row take the byte path below
+                        int a0[3], b0[3], a1[3], b1[3];
+                        auto fetch = [&](const uint8_t* row, int (&pa)[3], int (&pb)[3]) {
+                            const uintptr_t ad = reinterpret_cast<uintptr_t>(row + tx.x);
+                            const uint32_t* w = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
+                            const uint32_t sh = (uint32_t)(ad & 3) * 8u;
+                            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+                            const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+                            pa[0] = lo & 0xff; pa[1] = (lo >> 8) & 0xff; pa[2] = (lo >> 16) & 0xff;
+                            pb[0] = lo >> 24; pb[1] = hi & 0xff; pb[2] = (hi >> 8) & 0xff;
+                        };
+                        fetch(r0, a0, b0);
+                        fetch(r1, a1, b1);
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const int h0 = (int)__ldg(r0 + tx.i0 * 3 + c) * tx.c0 + (int)__ldg(r0 + tx.i1 * 3 + c) * tx.c1;
-                        const int h1 = (int)__ldg(r1 + tx.i0 * 3 + c) * tx.c0 + (int)__ldg(r1 + tx.i1 * 3 + c) * tx.c1;
-                        int r = (((ty.c0 * (h0 >> 4)) >> 16) + ((ty.c1 * (h1 >> 4)) >> 16) + 2) >> 2;
-                        v[c] = min(max(r, 0), 255);
+                        for (int c = 0; c < 3; ++c) {
+                            const int h0 = a0[c] * tx.z + b0[c] * tx.w;
+                            const int h1 = a1[c] * tx.z + b1[c] * tx.w;
+                            const int r = (((ty.c0 * (h0 >> 4)) >> 16) + ((ty.c1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                            vv[k][c] = min(max(r, 0), 255);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int h0 = (int)__ldg(r0 + tx.x + c) * tx.z + (int)__ldg(r0 + tx.y + c) * tx.w;
+                            const int h1 = (int)__ldg(r1 + tx.x + c) * tx.z + (int)__ldg(r1 + tx.y + c) * tx.w;
+                            const int r = (((ty.c0 * (h0 >> 4)) >> 16) + ((ty.c1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                            vv[k][c] = min(max(r, 0), 255);
+                        }
                     }
                 }
             }
-            const int c0 = swap_rb ? v[2] : v[0], c2 = swap_rb ? v[0] : v[2];
-            if (nchw) {
-                const size_t plane = (size_t)out_h * out_w;
-                T* o = out + (size_t)f * 3 * plane + (size_t)y * out_w + x;
-                o[0] = cvt<T>(c0); o[plane] = cvt<T>(v[1]); o[2 * plane] = cvt<T>(c2);
-            } else {
-                T* o = out + (((size_t)f * out_h + y) * out_w + x) * 3;
-                o[0] = cvt<T>(c0); o[1] = cvt<T>(v[1]); o[2] = cvt<T>(c2);
+            if (swap_rb) { const int tmp = vv[k][0]; vv[k][0] = vv[k][2]; vv[k][2] = tmp; }
+        }
+        if (packed) {
+            const size_t plane = (size_t)out_h * out_w;
+            T* o = out + (size_t)f * 3 * plane + (size_t)y * out_w + gx * 4;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                struct alignas(4 * sizeof(T)) Pack { T v[4]; } pk;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pk.v[k] = s_cvt[vv[k][c]];
+                *reinterpret_cast<Pack*>(o + c * plane) = pk;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int x = gx * 4 + k;
+                if (x >= out_w) break;
+                if (nchw) {
+                    const size_t plane = (size_t)out_h * out_w;
+                    T* o = out + (size_t)f * 3 * plane + (size_t)y * out_w + x;
+                    o[0] = s_cvt[vv[k][0]]; o[plane] = s_cvt[vv[k][1]]; o[2 * plane] = s_cvt[vv[k][2]];
+                } else {
+                    T* o = out + (((size_t)f * out_h + y) * out_w + x) * 3;
+                    o[0] = s_cvt[vv[k][0]]; o[1] = s_cvt[vv[k][1]]; o[2] = s_cvt[vv[k][2]];
+                }
             }
         }
     }
@@ -145,8 +203,18 @@ int launch_resize(hbp_ctx* ctx, const uint8_t* in, int n, int H, int W, void* ou
                   int pad_value, int nchw) {
     const size_t total = (size_t)n * out_h * ((out_w + 3) / 4);
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
-    resize_kernel<T><<<blocks, 256, 0, ctx->stream>>>(in, n, H, W, (T*)out, out_h, out_w, ox, oy, nw, nh,
-                                                      sx, sy, identity, swap_rb, pad_value, nchw);
+    const size_t smem = (size_t)((nw + 3) & ~3) * sizeof(int4) + 256 * sizeof(T);
+    if (smem > 48 * 1024) {
+        static bool attr_done[3] = {false, false, false};
+        const int ti = sizeof(T) == 1 ? 0 : sizeof(T) == 2 ? 1 : 2;
+        if (!attr_done[ti]) {
+            HBP_CUDA(cudaFuncSetAttribute(resize_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_done[ti] = true;
+        }
+        if (smem > 200 * 1024) { hbp_set_error("resize: output rows wider than %d pixels are not supported", (200 * 1024 - 1024) / 16); return HBP_ERR_INVALID; }
+    }
+    resize_kernel<T><<<blocks, 256, smem, ctx->stream>>>(in, n, H, W, (T*)out, out_h, out_w, ox, oy, nw, nh,
+                                                         sx, sy, identity, swap_rb, pad_value, nchw);
     HBP_LAUNCH_CHECK(ctx);
     return HBP_OK;
 }
