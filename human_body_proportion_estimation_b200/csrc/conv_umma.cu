@@ -83,6 +83,7 @@ struct ConvParams {
     uint32_t c_bytes;            // halo mode: constant operand tiles (ones, identity, bias) between the residual ring and the barriers
     uint32_t idesc32;            // instruction descriptor with N = 32 (residual MMAs)
     int reverse;                 // halo mode: the CTAs walk the tiles from the last to the first (tile = n_tiles - 1 - index)
+    int split_producer;          // halo mode, streamed weights: halo tiles are requested by warp 3 chunk by chunk, warp 0 only streams weights
     unsigned long long hint_a, hint_r;   // halo mode: L2 cache policies of the halo / residual TMA loads (kEvictNormal, kEvictFirst)
     unsigned long long hint_o;           // halo mode: L2 cache policy of the output stores (0 = plain stores)
     int dbg_flags;               // bring-up experiments: 1 = skip the output stores, 2 = skip the bias loads
@@ -762,7 +763,7 @@ constexpr int kMaxAStages = 4;   // halo tiles in flight per CTA
 constexpr int kMaxBSlots = 24;   // (3 dx) x 8 Cin chunks: weight slots of three taps each (resident) or ring depth (streamed)
 constexpr int kHaloThreads = 512;   // warp 0 halo + weight TMA, warps 1-2 MMA issuers (warp 1 owns TMEM), warp 3 residual TMA, warps 4-7 / 8-11 / 12-15 up to three epilogue teams
 constexpr int kMaxAccBufs = 4;
-constexpr uint32_t kHaloBarBytes = 8u * (kMaxAStages * kMaxChunks + 3 * kMaxAStages + 2 * kMaxBSlots + 2 * kMaxAccBufs) + 16u;
+constexpr uint32_t kHaloBarBytes = 8u * (2 * kMaxAStages * kMaxChunks + 3 * kMaxAStages + 2 * kMaxBSlots + 2 * kMaxAccBufs) + 16u;
 
 // 3x3 stride-1 convolution, halo mode, one persistent CTA per SM.  Tile = tn images x th rows
 // x 8 columns.  In shared memory a chunk is the TMA box (chunk channels, 10, rs = th+2, tn):
@@ -817,7 +818,8 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t acc_empty = acc_full + 8u * kMaxAccBufs;             // acc_bufs
     const uint32_t res_full = acc_empty + 8u * kMaxAccBufs;             // a_stages
     const uint32_t res_empty = res_full + 8u * kMaxAStages;             // a_stages
-    const uint32_t tmem_slot = res_empty + 8u * kMaxAStages;
+    const uint32_t a_cempty = res_empty + 8u * kMaxAStages;             // a_stages x n_chunks (streamed weights: chunks are handed back one by one)
+    const uint32_t tmem_slot = a_cempty + 8u * (kMaxAStages * kMaxChunks);
     float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + kHaloBarBytes - smem_u32(smem_raw)));
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
@@ -835,7 +837,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
             if (p.res_smem) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
         }
-        for (int i = lane; i < p.a_stages * p.n_chunks; i += 32) mbar_init(a_full + 8u * i, 1);
+        for (int i = lane; i < p.a_stages * p.n_chunks; i += 32) { mbar_init(a_full + 8u * i, 1); mbar_init(a_cempty + 8u * i, 1); }
         for (int i = lane; i < p.a_stages; i += 32) { mbar_init(a_empty + 8u * i, 1); mbar_init(res_full + 8u * i, 1); mbar_init(res_empty + 8u * i, p.res_mma ? 1 : 4); }
         for (int i = lane; i < p.b_slots; i += 32) { mbar_init(b_full + 8u * i, 1); mbar_init(b_empty + 8u * i, 1); }
         for (int i = lane; i < kMaxAccBufs; i += 32) { mbar_init(acc_full + 8u * i, 1); mbar_init(acc_empty + 8u * i, 4); }
@@ -915,8 +917,15 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
             __syncwarp();
         }
-        pdl_wait();                          // activations below are the previous launch's output
-        for (int t = 0; t < p.a_stages && t < T; ++t) issue_a(t);
+        // streamed weights (they do not fit beside a halo tile: the 128-channel branch, transition1): this warp does
+        // nothing but keep the weight ring full -- the halo tiles come from warp 3, chunk by chunk.  (With both on one warp
+        // the wait for a free halo stage sat between the weight requests of consecutive tiles: every tile started with an
+        // empty ring.)  Off by default (HBP_HALO_SPLIT_PRODUCER=1): measured gains only with the conv alone on the GPU.
+        const bool split = !p.b_resident && p.split_producer;
+        if (!split) {
+            pdl_wait();                      // activations below are the previous launch's output
+            for (int t = 0; t < p.a_stages && t < T; ++t) issue_a(t);
+        }
         int s = 0;
         uint32_t ph = 0;
         for (int j = 0; j < T; ++j) {
@@ -934,9 +943,44 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         if (++s == p.b_slots) { s = 0; ph ^= 1u; }
                     }
             }
-            if (j + p.a_stages < T) issue_a(j + p.a_stages);
+            if (!split && j + p.a_stages < T) issue_a(j + p.a_stages);
         }
     } else if (warp == 3) {
+        if (!p.b_resident && p.split_producer) {
+            // ===== halo + residual producer of the streamed-weights mode: chunk cc of stage sa is refilled as soon as
+            // the MMAs that read it have retired (a_cempty), i.e. a part of a tile ahead even with a single stage =====
+            const int T = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            TileWalk aw;
+            aw.init((int)blockIdx.x, (int)gridDim.x, p.tiles_w, p.tiles_h, p.n_tiles, p.reverse);
+            int sa = 0, lap = 0, sr = 0, lap_r = 0;
+            pdl_wait();
+            for (int t = 0; t < T; ++t) {
+                const int n0 = aw.tg * p.tn, h0 = aw.th * p.th, w0 = aw.tw * 8;
+                for (int cc = 0; cc < p.n_chunks; ++cc) {
+                    const int i = sa * p.n_chunks + cc;
+                    if (lap > 0) mbar_wait(a_cempty + 8u * i, (uint32_t)((lap - 1) & 1));
+                    if (elect_one()) {
+                        mbar_expect_tx(a_full + 8u * i, p.a_box_bytes);
+                        tma_load_4d_hint(a_base + sa * a_tile_bytes + cc * p.a_chunk_bytes, &tmA, a_full + 8u * i, cc * p.chunk, w0 - KS / 2, h0 - KS / 2, n0, p.hint_a);
+                    }
+                    __syncwarp();
+                    if (cc == 0 && p.res_smem) {
+                        // the tile's residual rows right behind its first chunk
+                        if (lap_r > 0) mbar_wait(res_empty + 8u * sr, (uint32_t)((lap_r - 1) & 1));
+                        if (elect_one()) {
+                            mbar_expect_tx(res_full + 8u * sr, (uint32_t)p.r_chunks * p.r_box_bytes);
+                            for (int rc = 0; rc < p.r_chunks; ++rc)
+                                tma_load_4d_hint(r_base + sr * r_tile_bytes + rc * p.r_chunk_bytes, &tmR, res_full + 8u * sr, n_off + rc * 64,
+                                                 aw.tw * 8, aw.th * p.th, aw.tg * p.tn, p.hint_r);
+                        }
+                        __syncwarp();
+                        if (++sr == p.a_stages) { sr = 0; ++lap_r; }
+                    }
+                }
+                if (++sa == p.a_stages) { sa = 0; ++lap; }
+                aw.next();
+            }
+        } else
         // ===== residual producer: the residual rows of every tile (no halo), 64 output channels per box,
         // through their own ring so that a slow epilogue never delays the halo requests =====
         if (p.res_smem) {
@@ -1043,6 +1087,10 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     }
                     __syncwarp();
                     if (!p.b_resident && ++s == p.b_slots) { s = 0; ph ^= 1u; }
+                }
+                if (!p.b_resident && p.split_producer) {
+                    if (elect_one()) umma_commit(a_cempty + 8u * (sa * p.n_chunks + cc));     // this chunk of the halo stage is free when its MMAs retire
+                    __syncwarp();
                 }
             }
             if (p.res_mma) {
@@ -2028,6 +2076,7 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
         p.hint_a = (op.in_dead && (l2_hints & 1)) ? kEvictFirst : kEvictNormal;
         p.hint_r = (op.res_dead && (l2_hints & 1)) ? kEvictFirst : kEvictNormal;
         p.hint_o = (op.out_keep && (l2_hints & 2)) ? kEvictLast : 0ull;
+        p.split_producer = env_int("HBP_HALO_SPLIT_PRODUCER", 0);   // (transition1 alone 72 -> 65 us, the 128-channel branch 9.75 -> 9.46 us on 148 SMs; nothing inside the network: off)
     }
     p.bias = m.d_bias + op.b_off;
     p.res = op.res >= 0 ? m.bufs[m.tensors[op.res].buf] : nullptr;

@@ -249,6 +249,18 @@ def test_nms_known_answers_and_ties(eng, golden):
         got = eng.yolo_nms(pred, 0.35, thr)
         for w, o in zip(want, got):
             assert np.array_equal(o, w)
+    # the three regimes of the sweep kernel (csrc/detect.cu: nms_sweep_gather_kernel): mask staged in shared memory with the
+    # removed words in registers (<= 1024 candidates), staged with more than 32 words, and on the mask in global memory
+    for k_cand in (40, 900, 1150, 2400):
+        p1 = pred[:1].copy()
+        _, src = detect.yolo_candidates(p1[0], 0.35)
+        assert len(src) >= k_cand
+        p1[0, src[k_cand:], 4] = 0.0                      # exactly k_cand candidates left
+        assert len(detect.yolo_candidates(p1[0], 0.35)[1]) == k_cand
+        for max_det in (300, 7):
+            want = detect.official_nms(p1, 0.35, 0.5, max_det=max_det)
+            got = eng.yolo_nms(p1, 0.35, 0.5, max_det=max_det)
+            assert np.array_equal(got[0], want[0]), (k_cand, max_det)
 
 
 def test_legacy_nms(eng, golden):
