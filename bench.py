@@ -469,8 +469,15 @@ def run_ours(args, rank, world, local_rank):
         eng.timer_start(1)
         check(lib.hbp_hrnet_forward(ctx, C.c_void_p(d_crops), cap, C.c_void_p(d_hm), F16, DEVICE))
         eng.timer_stop(1)
+        if os.environ.get("HBP_BENCH_DEBUG"):
+            try:
+                eng.sync()
+            except Exception:
+                sys.stderr.write("[bench debug] HRNet-only forward %d (0 = eager, 1 = graph capture, 2.. = replays) faulted\n" % i)
+                raise
         if i >= 3:
             hrnet_ms.append(eng.timer_ms(1))
+    eng.sync()                                     # (a device fault of this phase is reported here, not in the e2e phase below)
 
     # ---- e2e through the public API with host buffers (pinned), two batches in flight
     h_frames = [eng.pinned_empty(frames.shape, np.uint8) for _ in range(2)]
@@ -714,6 +721,7 @@ def main():
         sys.stderr.flush()
         if world > 1 or args.retried:
             raise
+        os.dup2(_REAL_STDOUT, 1)                   # the fresh process gets the caller's stdout back
         os.execv(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + ["--retried"])
 
 

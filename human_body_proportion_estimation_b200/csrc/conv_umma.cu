@@ -1942,7 +1942,8 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     const double l2_bpc = (double)env_int("HBP_HALO_L2BPC", 64);      // L2 -> shared memory bytes per clock and SM the cost model assumes
     struct Cand { int tn, th, m, n_tile; long items; double cost; };
     Cand best{0, 0, 0, 0, 0, 1e30};
-    for (int mt = 1; mt <= 2; ++mt)
+    const int mt_max = (env_int("HBP_HALO_C64_M1", 0) && op.cin == 64 && op.cout == 64 && ksz == 3 && op.sm_share > 0.f && (env_int("HBP_HALO_C64_M1", 0) > 1 || op.res >= 0)) ? 1 : 2;
+    for (int mt = 1; mt <= mt_max; ++mt)
         for (int n = 1; n <= 6; ++n)
             for (int h = Ho < 16 * mt ? Ho : 16 * mt; h >= 1; --h) {
                 if (Ho % h) continue;

@@ -1141,6 +1141,10 @@ int hrnet_forward(hbp_ctx* ctx, const __half* crops, int P, void* heatmaps, int 
         // second call with this key: capture it (plans and group tables exist since the eager first call, so nothing is
         // allocated or encoded inside the capture)
         cudaGraph_t g = nullptr;
+        // (nothing of the eager first call may still be in flight: the capture re-records the events of its fork / join
+        // edges; once per key, so the wait costs nothing in steady state)
+        HBP_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < kStreams - 1; ++i) if (m->side[i]) HBP_CUDA(cudaStreamSynchronize(m->side[i]));
         HBP_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         s = issue_ops(ctx, m, crops, P, heatmaps, out_dtype, &n);
         cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
