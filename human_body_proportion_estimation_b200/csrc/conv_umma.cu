@@ -761,7 +761,7 @@ constexpr int kHaloW = 10;       // 8 output columns + 1 halo column each side
 constexpr int kMaxChunks = 8;
 constexpr int kMaxAStages = 4;   // halo tiles in flight per CTA
 constexpr int kMaxBSlots = 24;   // (3 dx) x 8 Cin chunks: weight slots of three taps each (resident) or ring depth (streamed)
-constexpr int kHaloThreads = 512;   // warp 0 halo + weight TMA, warps 1-2 MMA issuers (warp 1 owns TMEM), warp 3 residual TMA, warps 4-7 / 8-11 / 12-15 up to three epilogue teams
+constexpr int kHaloThreads = 384;   // warp 0 halo + weight TMA, warps 1-2 MMA issuers (warp 1 owns TMEM), warp 3 residual TMA, warps 4-7 / 8-11 two epilogue teams
 constexpr int kMaxAccBufs = 4;
 constexpr uint32_t kHaloBarBytes = 8u * (2 * kMaxAStages * kMaxChunks + 3 * kMaxAStages + 2 * kMaxBSlots + 2 * kMaxAccBufs) + 16u;
 
@@ -2058,9 +2058,8 @@ static int plan_halo(hbp_ctx* ctx, HrnetModel& m, const HOp& op, int capP, UmmaP
     // stage s and accumulator buffer b are always served by the same issuer warp / epilogue team,
     // i.e. the issuer and team counts divide the stage and buffer counts.
     p.teams = (acc_bufs % 2 == 0 && a_stages % 2 == 0) ? 2 : 1;
-    // a third team (tile j -> team j % 3, accumulator buffer j % 4, ring stage j % a_stages: the barriers count warps, not
-    // teams) for the epilogue-bound shapes: many output columns per tile and few MMAs (layer1's 1x1 convs)
-    if (p.teams == 2 && acc_bufs >= 4 && a_stages >= 4 && per_cta >= 3 && n_tile >= env_int("HBP_HALO_TEAMS3_N", 64)) p.teams = env_int("HBP_HALO_TEAMS", 3);
+    // (a third epilogue team -- 512 threads, tile j -> team j % 3 -- gave no gain on the epilogue-heavy 1x1 convs, which are L2-byte bound, and
+    // faulted intermittently when two forwards shared the GPU: removed, profiles/r02_epilogue_ablation.md)
     p.issuers = (resident && p.teams >= 2 && per_cta > 1) ? env_int("HBP_HALO_ISSUERS", 2) : 1;
     if (a_stages % p.issuers || acc_bufs % p.issuers) p.issuers = 1;
     p.acc_bufs = acc_bufs; p.a_stages = a_stages; p.b_slots = b_slots; p.b_resident = resident;

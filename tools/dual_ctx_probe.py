@@ -48,5 +48,8 @@ def run(K, P, iters=30, warm=6):
 
 
 if __name__ == "__main__":
-    for K, P in ((1, 64), (2, 32), (4, 16), (1, 128), (2, 64), (1, 32)):
+    cases = ((1, 64), (2, 32), (4, 16), (1, 128), (2, 64), (1, 32))
+    if len(sys.argv) > 2:
+        cases = ((int(sys.argv[1]), int(sys.argv[2])),)
+    for K, P in cases:
         run(K, P)
