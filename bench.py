@@ -246,7 +246,8 @@ def config_dict(cfg):
             "person_slots_per_step_per_gpu": cfg["cap"],
             "hrnet": "W%d %dx%d" % (cfg["width"], cfg["in_h"], cfg["in_w"]), "weights": "random-init (seed 0), BN folded",
             "detector_outputs": "synthetic (the backbones are opaque artifacts outside the reference tree)",
-            "l2": "flushed between timed steps (256 MiB write)", "parallelism": "frame-sharded, no collective"}
+            "l2": "value / e2e: the steps cycle through resident input sets (frame + detector head) that together exceed the 126 MB L2; single_context, roofline and stage legs: L2 flushed before every timed step (256 MiB write)",
+            "parallelism": "frame-sharded, no collective"}
 
 
 # --------------------------------------------------------------------------
@@ -394,7 +395,7 @@ def run_ours(args, rank, world, local_rank):
 
     eng = Engine(local_rank)
     lib, ctx = eng._lib, eng._ctx
-    eng.load_hrnet(None, cfg["width"], cfg["in_h"], cfg["in_w"], seed=0)
+    hr_weights = eng.load_hrnet(None, cfg["width"], cfg["in_h"], cfg["in_w"], seed=0)
     frames, dets = synth_inputs(cfg)
     cap, F = cfg["cap"], cfg["frames"]
     thr = np.asarray(KEYPOINT_THRES_LIST, np.float32)
@@ -436,28 +437,73 @@ def run_ours(args, rank, world, local_rank):
     eng.sync()
     assert st_out.value == 0, "pipeline status %d" % st_out.value
 
+    # ---- `value`: whole-job throughput, inputs resident in HBM.  The streaming form of the product: HBP_E2E_CONTEXTS
+    # (default 2) engine contexts on this rank's GPU, steps alternating between them, two tickets in flight per context (the
+    # forward of one step overlaps the tail of the previous one).  The steps cycle through input sets that together
+    # exceed the 126 MB L2, so no step finds its frame or detector head cached.
+    n_ctx = max(1, int(os.environ.get("HBP_E2E_CONTEXTS", "2")))
+    pool_engines = [eng]
+    for _ in range(n_ctx - 1):
+        e2 = Engine(local_rank)
+        e2.load_hrnet(hr_weights, cfg["width"], cfg["in_h"], cfg["in_w"], seed=0)
+        pool_engines.append(e2)
+    set_bytes = frames.nbytes + sum(d.nbytes for d in dets)
+    n_sets = max(2, int(140e6 // set_bytes) + 2)
+    d_sets = [(d_frames, d_dets)] + [(eng.to_device(frames), [eng.to_device(d) for d in dets] + [None, None]) for _ in range(n_sets - 1)]
+
+    def dev_submit(i):
+        e = pool_engines[i % n_ctx]
+        fr, dd = d_sets[i % n_sets]
+        tk = C.c_int(-1)
+        check(lib.hbp_det_pose_submit(e._ctx, C.byref(prm_dev), C.c_void_p(fr), ptr(dd[0]), ptr(dd[1]), ptr(dd[2]),
+                                      ptr(hts), hts.size, ptr(thr), C.byref(tk)))
+        return e, tk.value
+
+    def dev_collect(e, tk):
+        check(lib.hbp_det_pose_collect(e._ctx, tk, C.byref(n_out), C.byref(st_out), None, None, None, None, None, None, None, None))
+        assert st_out.value == 0, "pipeline status %d" % st_out.value
+        return n_out.value
+
+    def dev_stream(n_steps):
+        inflight, crops = [], 0
+        for i in range(n_steps):
+            inflight.append(dev_submit(i))
+            if len(inflight) >= 2 * n_ctx:
+                crops += dev_collect(*inflight.pop(0))
+        for it in inflight:
+            crops += dev_collect(*it)
+        return crops
+
+    dev_stream(max(args.warmup, 3) * n_ctx)         # >= 3 warm-up steps per context (plans, graphs)
+    for e in pool_engines:
+        e.sync()
     sampler = ClockSampler(local_rank, period_ms=20) if rank == 0 else None
     barrier()
-    eng.sync()
     if sampler:
         sampler.mark()
-    launches0 = eng.kernel_launches()
-    step_ms = []
+    launches0 = sum(e.kernel_launches() for e in pool_engines)
     t_wall0 = time.perf_counter()
-    crops_done = 0
+    crops_done = dev_stream(args.steps)
+    for e in pool_engines:
+        e.sync()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    launches = sum(e.kernel_launches() for e in pool_engines) - launches0
+    clocks = sampler.stop() if sampler else None
+
+    # ---- one context, one step at a time (CUDA events around each step, L2 flushed before it): the per-step device time
+    # that the stage table and the roofline refer to
+    step_ms = []
+    single_crops = 0
     for _ in range(args.steps):
         eng.flush_l2()
         eng.timer_start(0)
         tk = step_device()
         eng.timer_stop(0)
-        crops_done += collect(tk)
+        single_crops += collect(tk)
         step_ms.append(eng.timer_ms(0))
     eng.sync()
-    barrier()
-    wall_ms = (time.perf_counter() - t_wall0) * 1e3
-    launches = eng.kernel_launches() - launches0
     dev_ms_total = sum(step_ms)
-    clocks = sampler.stop() if sampler else None
 
     # HRNet stage alone (CUDA events around hbp_hrnet_forward on the pipeline's own crop buffer shapes), for the roofline
     d_crops = eng.dev_alloc(cap * 3 * cfg["in_h"] * cfg["in_w"] * 2)
@@ -502,20 +548,38 @@ def run_ours(args, rank, world, local_rank):
         out = eng.det_pose_collect(submit_host(0))
         lat.append((time.perf_counter() - t1) * 1e3)
     e2e_steps = args.steps if args.steps < 5 else max(args.steps, 50)
+    # Throughput: the public streaming form -- MultiGpuEngine.det_pose_stream over HBP_E2E_CONTEXTS (default 2) engine
+    # contexts on this rank's GPU, two tickets in flight each, steps alternating between them.  Every step still uploads its
+    # frame + detector head from pinned memory and reads its results back.
+    from human_body_proportion_estimation_b200.engine import MultiGpuEngine
+    pool = MultiGpuEngine(engines=pool_engines)
+    pool_bufs = [(h_frames, h_dets)]
+    for e2 in pool_engines[1:]:
+        hf = [e2.pinned_empty(frames.shape, np.uint8) for _ in range(2)]
+        hd = [[e2.pinned_empty(d.shape, d.dtype) for d in dets] for _ in range(2)]
+        for k in range(2):
+            hf[k][...] = frames
+            for a, b in zip(hd[k], dets):
+                a[...] = b
+        pool_bufs.append((hf, hd))
+
+    def pool_submit(e, r, s):
+        hf, hd = pool_bufs[r]
+        k = s & 1
+        if cfg["detector"] == "yolo":
+            return e.det_pose_submit_yolo(hf[k], hd[k][0], person_height=HEIGHTS, persons_cap=cap, resample="bilinear")
+        return e.det_pose_submit_edet(hf[k], hd[k][0], hd[k][1], hd[k][2], person_height=HEIGHTS, persons_cap=cap, max_persons=16)
+
+    pool.det_pose_stream(pool_submit, 4 * n_ctx)              # warm-up of the additional contexts (plans, graphs)
     sampler2 = ClockSampler(local_rank, period_ms=250) if rank == 0 else None
     barrier()
     if sampler2:
         sampler2.mark()
     t0 = time.perf_counter()
-    prev, e2e_crops = None, 0
-    for i in range(e2e_steps):
-        tk = submit_host(i & 1)
-        if prev is not None:
-            e2e_crops += eng.det_pose_collect(prev)["n"]
-        prev = tk
-    out = eng.det_pose_collect(prev, return_heatmaps=True)
-    e2e_crops += out["n"]
+    res = pool.det_pose_stream(pool_submit, e2e_steps)
     e2e_s = time.perf_counter() - t0
+    e2e_crops = sum(r["n"] for r in res)
+    out = eng.det_pose_collect(submit_host(0), return_heatmaps=True)      # (checked against the oracle below)
     barrier()
     h2d = frames.nbytes + sum(d.nbytes for d in dets) + hts.nbytes + 17 * 4 + 64
     d2h = 64 + cap * (8 + 4 + 16 + 17 * 8 + 17 * 4 + 4 + 44)
@@ -528,7 +592,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- max over ranks (device time, e2e wall time)
     dev_ms_total, e2e_s, wall_ms = grp.max_over_ranks([dev_ms_total, e2e_s, wall_ms])
     launches = int(grp.sum_over_ranks([launches])[0])
-    crops_all = grp.sum_over_ranks([crops_done, e2e_crops])
+    crops_all = grp.sum_over_ranks([crops_done, e2e_crops, single_crops])
     if rank != 0:
         grp.close()
         return
@@ -572,7 +636,8 @@ def run_ours(args, rank, world, local_rank):
     hr_ms = statistics.mean(hrnet_ms)
     achieved = flops_crop * cap / (hr_ms * 1e-3) / 1e12
     n_launch_step = max(1, int(launches) // max(1, world) // args.steps)
-    value = crops_all[0] / (dev_ms_total * 1e-3)
+    value = crops_all[0] / (wall_ms * 1e-3)
+    single_value = crops_all[2] / (dev_ms_total * 1e-3)
     e2e_val = crops_all[1] / e2e_s
 
     stage_rf = None
@@ -597,14 +662,18 @@ def run_ours(args, rank, world, local_rank):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_total / args.steps, "higher_is_better": True,
+        "warmup": max(args.warmup, 3), "ms_per_step": wall_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": config_dict(cfg),
         "crops_per_step_per_gpu": n_live,
-        "wall_ms_per_step": wall_ms / args.steps,
+        "contexts_per_gpu": n_ctx,
+        "timing": "barrier + synchronize on both sides of exactly K steps; K steps / that time, max over ranks",
+        "single_context": {"value": single_value, "unit": UNIT, "ms_per_step": dev_ms_total / args.steps,
+                           "note": "one engine context, one step at a time, CUDA events around each step, L2 flushed before it"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "p50_batch_latency_ms": statistics.median(lat), "steps": e2e_steps,
-                "api": "Engine.det_pose_submit_%s / det_pose_collect (hbp_det_pose_submit/_collect), two batches in flight; latency from one synchronous submit+collect at a time" % cfg["detector"]},
+                "contexts_per_gpu": n_ctx,
+                "api": "MultiGpuEngine.det_pose_stream over %d engine context(s) on the GPU: Engine.det_pose_submit_%s / det_pose_collect (hbp_det_pose_submit/_collect), two tickets in flight per context; latency from one synchronous submit+collect at a time" % (n_ctx, cfg["detector"])},
         "parity_check": parity,
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "HRNet conv stack (conv_umma_halo_kernel, conv_umma_pgroup_kernel, conv_umma_kernel, upsample_add_group, stem, head; one CUDA graph), %d person slots; the whole chain is %d launches per step" % (cap, n_launch_step),

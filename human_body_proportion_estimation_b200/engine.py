@@ -479,7 +479,11 @@ class MultiGpuEngine:
     unit = frame (+ its persons); frame f -> GPU f mod G; results concatenated
     on the host in frame order.  No collective, no peer traffic."""
 
-    def __init__(self, devices=None, **hrnet_kw):
+    def __init__(self, devices=None, engines=None, **hrnet_kw):
+        if engines is not None:                     # ready-made engines (HRNet already loaded)
+            self.engines = list(engines)
+            self._hrnet_kw = hrnet_kw
+            return
         if devices is None:
             n = C.c_int()
             check(_capi.lib().hbp_device_count(C.byref(n)))
@@ -539,6 +543,27 @@ class MultiGpuEngine:
             for k, v in out.items():
                 merged[k][sel] = v
         return merged
+
+    def det_pose_stream(self, submit, n_steps, depth=2, collect_kw=None):
+        """Chained det->pose steps (hbp_det_pose_submit/_collect) round robin over the engines, `depth` (<= 2) tickets in
+        flight per engine, driven from the calling thread (submits only enqueue).  `submit(engine, rank, step)` -> ticket, e.g.
+        `lambda e, r, s: e.det_pose_submit_yolo(frame[r][s & 1], head[r][s & 1], persons_cap=64)` with per-engine pinned
+        buffers.  The engines may be several contexts on ONE GPU -- `MultiGpuEngine(devices=[0, 0])`: each context has its
+        own streams, activation buffers and graphs, so the forward of one step overlaps the tail of the previous one
+        (+8 % steps/s on a B200: tools/dual_engine_e2e.py).  Returns the results in step order."""
+        G = len(self.engines)
+        results = [None] * n_steps
+        inflight = []                               # (step, engine, ticket)
+        kw = collect_kw or {}
+        for s in range(n_steps):
+            e = self.engines[s % G]
+            inflight.append((s, e, submit(e, s % G, s // G)))
+            if len(inflight) >= depth * G:
+                g, eg, tk = inflight.pop(0)
+                results[g] = eg.det_pose_collect(tk, **kw)
+        for g, eg, tk in inflight:
+            results[g] = eg.det_pose_collect(tk, **kw)
+        return results
 
     def stream(self, frame_source, n_frames, depth=2):
         """Frame stream sharded over the GPUs (BASELINE configs[4]): frame f goes to GPU f mod G, every GPU keeps
