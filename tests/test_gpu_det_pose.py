@@ -90,6 +90,29 @@ def test_chain_yolo_config2(eng):
     assert eng.det_pose_collect(tk)["status"] & 1
 
 
+def test_det_pose_stream_two_contexts_on_one_gpu(eng):
+    """MultiGpuEngine(devices=[0, 0]).det_pose_stream: steps alternate between two engine contexts on the same GPU (their
+    forwards overlap); every step's outputs equal the single-engine call on the same inputs, in step order."""
+    from human_body_proportion_estimation_b200.engine import MultiGpuEngine
+    eng.load_hrnet(None, 32, 256, 192, seed=0)
+    pred, _ = synth.yolo_decoded_head()
+    frames = [synth.frame_u8(H, W, seed=synth.SEED_BASE + 30 + i) for i in range(3)]
+    heights = [180.0, 165.0, 172.5]
+    want = [eng.det_pose_collect(eng.det_pose_submit_yolo(f, pred, person_height=heights, persons_cap=48)) for f in frames]
+    pool = MultiGpuEngine(devices=[0, 0], width=32, in_h=256, in_w=192, seed=0)
+    n_steps = 9
+    got = pool.det_pose_stream(lambda e, r, s: e.det_pose_submit_yolo(frames[(s * 2 + r) % 3], pred, person_height=heights, persons_cap=48),
+                               n_steps, depth=2)
+    assert len(got) == n_steps
+    for step, g in enumerate(got):
+        w = want[step % 3]                      # step -> engine step % 2, per-engine step step // 2: frame (s*2 + r) % 3 = step % 3
+        assert g["n"] == w["n"] and g["status"] == 0
+        for k in KEYS + ("boxes_yxyx_px",):
+            assert np.array_equal(g[k], w[k], equal_nan=True), (step, k)
+    for e in pool.engines:
+        e.close()
+
+
 def test_chain_edet_config3(eng):
     """configs[3]: 16 frames 1080p, synthetic EfficientDet outputs, up to 16 persons per frame, HRNet-W48 384x288"""
     from oracle import detect as od
