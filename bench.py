@@ -697,7 +697,8 @@ def stream_config4(n_gpus, frames=160, warmup=16, persons=100):
     from human_body_proportion_estimation_b200 import geometry, synth
     from human_body_proportion_estimation_b200.engine import MultiGpuEngine
     H, W = 2160, 3840
-    mg = MultiGpuEngine(list(range(n_gpus)), width=32, in_h=256, in_w=192, seed=0)
+    n_ctx = max(1, int(os.environ.get("HBP_E2E_CONTEXTS", "2")))
+    mg = MultiGpuEngine([d for d in range(n_gpus) for _ in range(n_ctx)], width=32, in_h=256, in_w=192, seed=0)   # n_ctx engine contexts per GPU
     base = [synth.frame_u8(H, W, seed=synth.SEED_BASE + 50 + i, smooth=False) for i in range(4)]
     pinned = []
     for e in mg.engines:
@@ -712,13 +713,13 @@ def stream_config4(n_gpus, frames=160, warmup=16, persons=100):
         boxes = synth.person_boxes_yxyx_px(persons, H, W, seed=synth.SEED_BASE + 60 + i, hmin=150, hmax=600)
         mats = geometry.crop_and_resize_matrices(boxes / np.array([H, W, H, W], np.float32), H, W, 256, 192)
         sets.append((mats.reshape(-1, 6), boxes))
-    G = n_gpus
+    G = n_gpus * n_ctx                      # engines: frame f -> engine f mod G (GPU (f mod G) // n_ctx)
 
     def source(f):
         mats, boxes = sets[f % 4]
         return pinned[f % G][(f // G) % 4], mats, boxes, 175.0
 
-    n = frames * G
+    n = frames * n_gpus
     mg.stream(source, warmup * G)
     t0 = time.perf_counter()
     res, lat = mg.stream(source, n)
@@ -734,8 +735,8 @@ def stream_config4(n_gpus, frames=160, warmup=16, persons=100):
     lat = np.sort(np.asarray(lat))
     for e in mg.engines:
         e.close()
-    return {"workload": "configs[4]: 4K frames (2160x3840x3 u8, pinned), %d persons/frame, HRNet-W32 256x192, ONE process, frame f -> GPU f mod G" % persons,
-            "n_gpus": G, "frames": n, "crops_per_s": n * persons / dt, "frames_per_s": n / dt,
+    return {"workload": "configs[4]: 4K frames (2160x3840x3 u8, pinned), %d persons/frame, HRNet-W32 256x192, ONE process, frame f -> engine f mod (GPUs x contexts per GPU)" % persons,
+            "n_gpus": n_gpus, "contexts_per_gpu": n_ctx, "frames": n, "crops_per_s": n * persons / dt, "frames_per_s": n / dt,
             "p50_frame_latency_ms_two_in_flight": float(lat[len(lat) // 2]), "p95_frame_latency_ms_two_in_flight": float(lat[int(len(lat) * 0.95)]),
             "p50_frame_latency_ms_synchronous": float(np.median(sync_lat)),
             "api": "MultiGpuEngine.stream (hbp_pose_pipeline_submit/_collect)"}
