@@ -524,6 +524,25 @@ def run_ours(args, rank, world, local_rank):
         if i >= 3:
             hrnet_ms.append(eng.timer_ms(1))
     eng.sync()                                     # (a device fault of this phase is reported here, not in the e2e phase below)
+    # the same forward on every context of the pool at once (what the streaming form does to the conv stack)
+    hr_pool_ms = None
+    if n_ctx > 1:
+        bufs = [(d_crops, d_hm)]
+        for e2 in pool_engines[1:]:
+            dc = e2.dev_alloc(cap * 3 * cfg["in_h"] * cfg["in_w"] * 2)
+            check(lib.hbp_memset_dev(e2._ctx, C.c_void_p(dc), 0, cap * 3 * cfg["in_h"] * cfg["in_w"] * 2))
+            bufs.append((dc, e2.dev_alloc(cap * 17 * (cfg["in_h"] // 4) * (cfg["in_w"] // 4) * 2)))
+        reps = 3 + min(args.steps, 10)
+        for i in range(3 + reps):
+            if i == 3:
+                for e in pool_engines:
+                    e.sync()
+                t_p = time.perf_counter()
+            for e, (dc, dh) in zip(pool_engines, bufs):
+                check(lib.hbp_hrnet_forward(e._ctx, C.c_void_p(dc), cap, C.c_void_p(dh), F16, DEVICE))
+        for e in pool_engines:
+            e.sync()
+        hr_pool_ms = (time.perf_counter() - t_p) * 1e3 / (reps * n_ctx)
 
     # ---- e2e through the public API with host buffers (pinned), two batches in flight
     h_frames = [eng.pinned_empty(frames.shape, np.uint8) for _ in range(2)]
@@ -680,7 +699,11 @@ def run_ours(args, rank, world, local_rank):
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                      "peak_source": pk["src"], "traffic": hrnet_traffic().get("dram_bytes_per_launch"),
                      "traffic_note": hrnet_traffic().get("note"),
-                     "flop_per_step": flops_crop * cap, "hrnet_ms": hr_ms},
+                     "flop_per_step": flops_crop * cap, "hrnet_ms": hr_ms,
+                     "streaming": None if not hr_pool_ms else {
+                         "note": "the same forward on %d engine contexts at once (host clock over %d forwards, no L2 flush): time per forward and the fraction of the peak it corresponds to" % (n_ctx, (3 + min(args.steps, 10)) * n_ctx),
+                         "hrnet_ms_per_forward": hr_pool_ms, "achieved": flops_crop * cap / (hr_pool_ms * 1e-3) / 1e12,
+                         "frac": flops_crop * cap / (hr_pool_ms * 1e-3) / 1e12 / pk["tflops"]}},
         "cpu_baseline": cpu,
         "stages_ms": stages,
         "stage_rooflines": stage_rf,
