@@ -468,10 +468,9 @@ void launch_filter(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float 
 int launch_nms_tail(hbp_ctx* ctx, const Cand* cand, const int* cand_count, SortedBox* sorted, int* n_sorted, uint32_t* mask,
                     int* keep, int* keep_count, int B, int cap, int n_max, int words_cap, size_t mask_img_stride, double thr,
                     int legacy, int max_nms, int max_keep, int* status, float* out_det, int* out_count) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!(ctx->attr_flags & ATTR_NMS)) {            // (function attributes are per device: one flag per context, not a process-wide static)
         HBP_CUDA(cudaFuncSetAttribute(nms_sweep_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSgSmemWords * 4)));
-        attr_done = true;
+        ctx->attr_flags |= ATTR_NMS;
     }
     const int rank_blocks = std::min((n_max + kRankWarps - 1) / kRankWarps, 2 * ctx->sm_count);
     launch_chained(rank_scatter_kernel, dim3(std::max(rank_blocks, 1), B), dim3(32 * kRankWarps), 0, ctx->stream, cand, cand_count, cap, legacy, max_nms,

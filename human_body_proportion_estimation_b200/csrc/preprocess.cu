@@ -205,11 +205,10 @@ int launch_resize(hbp_ctx* ctx, const uint8_t* in, int n, int H, int W, void* ou
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
     const size_t smem = (size_t)((nw + 3) & ~3) * sizeof(int4) + 256 * sizeof(T);
     if (smem > 48 * 1024) {
-        static bool attr_done[3] = {false, false, false};
-        const int ti = sizeof(T) == 1 ? 0 : sizeof(T) == 2 ? 1 : 2;
-        if (!attr_done[ti]) {
+        const uint32_t flag = sizeof(T) == 1 ? ATTR_RESIZE_U8 : sizeof(T) == 2 ? ATTR_RESIZE_F16 : ATTR_RESIZE_F32;   // per device
+        if (!(ctx->attr_flags & flag)) {
             HBP_CUDA(cudaFuncSetAttribute(resize_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done[ti] = true;
+            ctx->attr_flags |= flag;
         }
         if (smem > 200 * 1024) { hbp_set_error("resize: output rows wider than %d pixels are not supported", (200 * 1024 - 1024) / 16); return HBP_ERR_INVALID; }
     }

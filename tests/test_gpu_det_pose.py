@@ -99,13 +99,19 @@ def test_det_pose_stream_two_contexts_on_one_gpu(eng):
     frames = [synth.frame_u8(H, W, seed=synth.SEED_BASE + 30 + i) for i in range(3)]
     heights = [180.0, 165.0, 172.5]
     want = [eng.det_pose_collect(eng.det_pose_submit_yolo(f, pred, person_height=heights, persons_cap=48)) for f in frames]
-    pool = MultiGpuEngine(devices=[0, 0], width=32, in_h=256, in_w=192, seed=0)
-    n_steps = 9
-    got = pool.det_pose_stream(lambda e, r, s: e.det_pose_submit_yolo(frames[(s * 2 + r) % 3], pred, person_height=heights, persons_cap=48),
+    import ctypes as C
+    from human_body_proportion_estimation_b200 import _capi
+    n_dev = C.c_int()
+    _capi.check(_capi.lib().hbp_device_count(C.byref(n_dev)))
+    devices = [d for d in range(min(n_dev.value, 2)) for _ in range(2)]        # two contexts on each of (up to) two GPUs
+    pool = MultiGpuEngine(devices=devices, width=32, in_h=256, in_w=192, seed=0)
+    G = len(devices)
+    n_steps = 4 * G + 1
+    got = pool.det_pose_stream(lambda e, r, s: e.det_pose_submit_yolo(frames[(s * G + r) % 3], pred, person_height=heights, persons_cap=48),
                                n_steps, depth=2)
     assert len(got) == n_steps
     for step, g in enumerate(got):
-        w = want[step % 3]                      # step -> engine step % 2, per-engine step step // 2: frame (s*2 + r) % 3 = step % 3
+        w = want[step % 3]                      # step -> engine step % G, per-engine step step // G: frame (s*G + r) % 3 = step % 3
         assert g["n"] == w["n"] and g["status"] == 0
         for k in KEYS + ("boxes_yxyx_px",):
             assert np.array_equal(g[k], w[k], equal_nan=True), (step, k)
