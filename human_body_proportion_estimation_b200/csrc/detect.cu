@@ -453,10 +453,108 @@ nms_sweep_gather_kernel(const uint32_t* __restrict__ mask, const int* __restrict
     }
 }
 
+// Latency form of the candidate filter (a few frames): a CTA copies its kStreamRows rows -- one contiguous span of the head --
+// into shared memory with coalesced 16-byte loads (all of them in flight at once: one memory round trip for the whole head
+// instead of a chain of strided sector reads per flagged row), then one thread per row tests the objectness and, for the ~4 %
+// of rows that pass, walks the class scores out of shared memory (row stride 5 + nc words: conflict-free for odd strides).
+// One counter atomic per CTA.  It moves the whole head (8.6 MB for 25200 x 85) where the sector-wise kernel above moves a
+// tenth of it, which is why large batches keep the other one.
+constexpr int kStreamRows = 256;
+__global__ void __launch_bounds__(kStreamRows)
+yolo_filter_stream_kernel(const float* __restrict__ pred, int N, int nc, float conf_thres, int legacy,
+                          const int* __restrict__ classes, int n_classes, Cand* __restrict__ cand,
+                          int* __restrict__ cand_count, int cap) {
+    extern __shared__ __align__(16) unsigned char s_rows_raw[];
+    __shared__ int s_warp_n[kStreamRows / 32];
+    __shared__ int s_base;
+    pdl_trigger();
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int E = 5 + nc;
+    const int r0 = blockIdx.x * kStreamRows;
+    const int rows = min(kStreamRows, N - r0);
+    const unsigned char* gbytes = reinterpret_cast<const unsigned char*>(pred + ((size_t)b * N + r0) * E);
+    const size_t span = (size_t)rows * E * sizeof(float);
+    const size_t lead = reinterpret_cast<uintptr_t>(gbytes) & 15;              // the span keeps its 16-byte phase in shared memory
+    const unsigned char* g0 = gbytes - lead;
+    const size_t vecs = (lead + span + 15) / 16;
+    // (the aligned vectors may reach up to 15 bytes before / after the span: still inside the allocation unless the span is
+    // the very first / last bytes of it -- those two vectors are read bytewise)
+    const unsigned char* t_begin = reinterpret_cast<const unsigned char*>(pred);
+    const unsigned char* t_end = reinterpret_cast<const unsigned char*>(pred + (size_t)gridDim.y * N * E);
+    for (size_t v = tid; v < vecs; v += kStreamRows) {
+        const unsigned char* ga = g0 + 16 * v;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (ga >= t_begin && ga + 16 <= t_end) q = __ldg(reinterpret_cast<const uint4*>(ga));
+        else {
+            unsigned char* qb = reinterpret_cast<unsigned char*>(&q);
+            for (int k = 0; k < 16; ++k) if (ga + k >= t_begin && ga + k < t_end) qb[k] = __ldg(ga + k);
+        }
+        *reinterpret_cast<uint4*>(s_rows_raw + 16 * v) = q;
+    }
+    __syncthreads();
+    const float* srow = reinterpret_cast<const float*>(s_rows_raw + lead) + (size_t)tid * E;
+    bool ok = false;
+    float best = -INFINITY, o = 0.f;
+    int best_j = 0x7fffffff;
+    if (tid < rows) {
+        o = srow[4];
+        if (legacy ? (o >= conf_thres) : (o > conf_thres)) {
+            // first-max over classes of (cls*obj) [official] or cls [legacy]; torch.max: NaN propagates as the max, first index on ties
+            for (int j = 0; j < nc; ++j) {
+                float c = srow[5 + j];
+                if (!legacy) c = __fmul_rn(c, o);
+                if (j == 0) { best = c; best_j = 0; }
+                else if (c > best || (c != c && best == best)) { best = c; best_j = j; }
+            }
+            ok = legacy ? true : (best > conf_thres);
+            if (ok && n_classes > 0) {
+                ok = false;
+                for (int k = 0; k < n_classes; ++k) ok |= ((float)best_j == (float)classes[k]);
+            }
+        }
+    }
+    const unsigned okm = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_warp_n[wrp] = __popc(okm);
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < kStreamRows / 32; ++w) { const int c = s_warp_n[w]; s_warp_n[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(cand_count + b, tot) : 0;
+    }
+    __syncthreads();
+    if (ok) {
+        const int slot = s_base + s_warp_n[wrp] + __popc(okm & ((1u << lane) - 1u));
+        if (slot < cap) {
+            const float cx = srow[0], cy = srow[1], w = srow[2], h = srow[3];
+            const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+            Cand c;
+            c.x1 = __fsub_rn(cx, hw); c.y1 = __fsub_rn(cy, hh);
+            c.x2 = __fadd_rn(cx, hw); c.y2 = __fadd_rn(cy, hh);
+            c.conf = legacy ? o : best;
+            c.cls = (float)best_j;
+            c.aux = best;
+            c.src = r0 + tid;
+            cand[(size_t)b * cap + slot] = c;
+        }
+    }
+}
+
 void launch_filter(hbp_ctx* ctx, const float* pred, int B, int N, int nc, float conf, int legacy, const int* classes,
                    int n_classes, Cand* cand, int* cand_count, int cap) {
     // a few frames: two warps per CTA (~100 CTAs for one 25200-row head: the kernel is a chain of strided-load round
     // trips, it needs SMs, not threads); large batches: eight
+    static const int stream_max_b = getenv("HBP_FILTER_STREAM_MAXB") ? atoi(getenv("HBP_FILTER_STREAM_MAXB")) : 8;
+    const size_t smem = (size_t)kStreamRows * (5 + nc) * sizeof(float) + 32;
+    bool stream_ok = B <= stream_max_b && smem <= 200 * 1024;
+    if (stream_ok && !(ctx->attr_flags & ATTR_FILTER)) {
+        if (cudaFuncSetAttribute(yolo_filter_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess) ctx->attr_flags |= ATTR_FILTER;
+        else { cudaGetLastError(); stream_ok = false; }
+    }
+    if (stream_ok) {
+        dim3 grid((N + kStreamRows - 1) / kStreamRows, B);
+        yolo_filter_stream_kernel<<<grid, kStreamRows, smem, ctx->stream>>>(pred, N, nc, conf, legacy, classes, n_classes, cand, cand_count, cap);
+        return;
+    }
     const int warps = (N + 32 * kFilterUnroll - 1) / (32 * kFilterUnroll);
     const int wpb = B >= 16 ? 8 : 2;
     dim3 grid((warps + wpb - 1) / wpb, B);

@@ -53,7 +53,7 @@ struct hbp_ctx {
     uint64_t pipe_seq = 0;
 };
 
-enum { ATTR_CROP = 1, ATTR_CONV = 2, ATTR_UMMA = 4, ATTR_NMS = 8, ATTR_PIL = 16, ATTR_RESIZE_U8 = 32, ATTR_RESIZE_F16 = 64, ATTR_RESIZE_F32 = 128 };
+enum { ATTR_CROP = 1, ATTR_CONV = 2, ATTR_UMMA = 4, ATTR_NMS = 8, ATTR_PIL = 16, ATTR_RESIZE_U8 = 32, ATTR_RESIZE_F16 = 64, ATTR_RESIZE_F32 = 128, ATTR_FILTER = 256 };
 
 // scratch slot ids
 enum {
