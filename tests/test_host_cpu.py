@@ -160,3 +160,33 @@ def test_reference_arm_does_not_load_the_library():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.strip().endswith("clean")
+
+
+def test_det_pose_stream_order_and_depth_with_fake_engines():
+    """MultiGpuEngine.det_pose_stream: step s goes to engine s mod G with per-engine step s // G, at most depth tickets are
+    outstanding per engine, results come back in step order (host logic only: the engines are stand-ins)."""
+    from human_body_proportion_estimation_b200.engine import MultiGpuEngine
+
+    class Fake:
+        def __init__(self, rank):
+            self.rank, self.out, self.max_out = rank, 0, 0
+
+        def submit(self, step):
+            self.out += 1
+            self.max_out = max(self.max_out, self.out)
+            return (self.rank, step)
+
+        def det_pose_collect(self, ticket, **kw):
+            self.out -= 1
+            return {"n": 1, "ticket": ticket, "kw": kw}
+
+    for G, depth, n in ((2, 2, 11), (3, 1, 7), (1, 2, 5)):
+        engs = [Fake(r) for r in range(G)]
+        pool = MultiGpuEngine(engines=engs)
+        seen = []
+        res = pool.det_pose_stream(lambda e, r, s: (seen.append((r, s)), e.submit(s))[1], n, depth=depth,
+                                   collect_kw={"return_heatmaps": False})
+        assert [r["ticket"] for r in res] == [(s % G, s // G) for s in range(n)]
+        assert seen == [(s % G, s // G) for s in range(n)]
+        assert all(e.out == 0 and e.max_out <= depth for e in engs)
+        assert res[0]["kw"] == {"return_heatmaps": False}
