@@ -130,7 +130,9 @@ HBP_API int hbp_yolo_filter(hbp_ctx* ctx, const float* pred, int B, int N, int n
  * out_det: (B,max_out,7) rows [x1,y1,x2,y2,obj,cls_conf,cls] grouped by class
  * ascending, obj-descending inside a class; out_count[b] = -1 when image b had
  * no candidate (the reference leaves None).  The reference's in-place rewrite
- * of pred[..., :4] to corners (:47) is done by the Python wrapper. */
+ * of pred[..., :4] to corners (:47) is done by the Python wrapper.
+ * Rows are EXACTLY 5 + nc floats wide (row stride = 5 + nc): a head with more columns than the classes the caller wants
+ * (the reference slices [:, 5:5+num_classes], :59) must be sliced to that width first -- Engine.yolo_nms_legacy does. */
 HBP_API int hbp_yolo_nms_legacy(hbp_ctx* ctx, const float* pred, int B, int N, int nc,
                         float conf_thres, float nms_thres, int max_out,
                         float* out_det, int* out_count, int mem);
