@@ -479,7 +479,9 @@ class MultiGpuEngine:
     unit = frame (+ its persons); frame f -> GPU f mod G; results concatenated
     on the host in frame order.  No collective, no peer traffic."""
 
-    def __init__(self, devices=None, engines=None, **hrnet_kw):
+    def __init__(self, devices=None, engines=None, contexts_per_gpu=1, **hrnet_kw):
+        """devices: GPU ids (default: all); contexts_per_gpu > 1 puts that many engine contexts on every listed GPU (the
+        list may also name a GPU several times itself); engines: ready-made Engine objects instead."""
         if engines is not None:                     # ready-made engines (HRNet already loaded)
             self.engines = list(engines)
             self._hrnet_kw = hrnet_kw
@@ -488,6 +490,7 @@ class MultiGpuEngine:
             n = C.c_int()
             check(_capi.lib().hbp_device_count(C.byref(n)))
             devices = list(range(n.value))
+        devices = [d for d in devices for _ in range(max(1, int(contexts_per_gpu)))]
         self.engines = [Engine(d) for d in devices]
         self._hrnet_kw = hrnet_kw
         weights = None
