@@ -8,13 +8,13 @@
 //   EfficientDet filter ... models/conv.py:22-57 (reference root)
 //
 // NMS pipeline, all on the device, no host round trip:
-//   1. filter    one warp per 32 rows: lanes test obj > conf on their own row
-//                (strided 4-byte reads), then the warp walks the flagged rows
-//                together: coalesced class scores, cls*obj, first-max class via
-//                shuffles, conf > thr, class filter, append to the candidate list.
-//   2. rank      stable order = (conf desc, source row asc); every candidate
-//                counts the candidates that precede it (all pairs, tiled through
-//                shared memory) and scatters itself to its rank.
+//   1. filter    obj > conf per row, then for the rows that pass: cls*obj, first-max class (torch.max order), conf > thr,
+//                class filter, append to the candidate list (order arbitrary: step 2 sorts).  Two forms with the same
+//                per-row arithmetic: up to 8 frames every CTA streams its 256 rows through shared memory with coalesced
+//                16-byte loads (yolo_filter_stream_kernel: one memory round trip for the whole head); large batches read
+//                only the objectness sector of every row and the flagged rows (yolo_filter_kernel: a tenth of the bytes).
+//   2. rank      stable order = (conf desc, source row asc); one warp per candidate counts the candidates that precede
+//                it (its lanes split the others) and scatters it to its rank.
 //   3. mask      bit (i,j), j>i, set iff IoU(i,j) > thr on the class-offset
 //                boxes; one warp per (row, 32-column word) builds the word with
 //                a ballot.  IoU in torchvision's operation order with explicit
@@ -26,8 +26,8 @@
 //                shared-memory read per lane and a shuffle -- then all threads write [x1,y1,x2,y2,conf,cls] of the kept
 //                boxes (un-offset).  Stops after max_det keeps.
 // Grids are sized on the host without knowing the candidate count (the kernels read it on the device and stride); the
-// launches are chained with programmatic dependent launch.  One 25200 x 85 head, 64 persons kept: 85 -> 49 us
-// (filter ~15, rank 6, mask 5, sweep + gather 13, launch gaps).
+// launches are chained with programmatic dependent launch.  One 25200 x 85 head, 64 persons kept: 131 us (round 1) -> 38 us
+// (profiles/r02_nms_kernels.md).
 // The legacy variant reuses 2-4 with key (class asc, obj desc, row asc), the
 // +1-pixel IoU, "suppress unless iou < thr" and same-class-only suppression.
 #include "hbp_internal.cuh"
