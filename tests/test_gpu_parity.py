@@ -249,6 +249,18 @@ def test_nms_known_answers_and_ties(eng, golden):
         got = eng.yolo_nms(pred, 0.35, thr)
         for w, o in zip(want, got):
             assert np.array_equal(o, w)
+    # rows whose byte span is not 16-byte aligned (E = 7 floats, N = 1001, three images): the streaming filter's unaligned
+    # head / tail vectors, and a batch of 9 images for the sector-wise filter on the same data
+    for B_ in (3, 9):
+        pu = np.zeros((B_, 1001, 5 + 2), np.float32)
+        pu[..., 0:2] = rng.integers(20, 620, (B_, 1001, 2))
+        pu[..., 2:4] = rng.integers(4, 80, (B_, 1001, 2)) * 2
+        pu[..., 4] = np.round(rng.uniform(0.2, 1, (B_, 1001)), 2)
+        pu[..., 5:] = np.round(rng.uniform(0.3, 1, (B_, 1001, 2)), 1)
+        want = detect.official_nms(pu, 0.35, 0.5)
+        got = eng.yolo_nms(pu, 0.35, 0.5)
+        for w, o in zip(want, got):
+            assert np.array_equal(o, w), B_
     # the three regimes of the sweep kernel (csrc/detect.cu: nms_sweep_gather_kernel): mask staged in shared memory with the
     # removed words in registers (<= 1024 candidates), staged with more than 32 words, and on the mask in global memory
     for k_cand in (40, 900, 1150, 2400):
