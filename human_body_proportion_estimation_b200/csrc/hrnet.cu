@@ -1141,8 +1141,9 @@ int hrnet_forward(hbp_ctx* ctx, const __half* crops, int P, void* heatmaps, int 
         // second call with this key: capture it (plans and group tables exist since the eager first call, so nothing is
         // allocated or encoded inside the capture)
         cudaGraph_t g = nullptr;
-        // (nothing of the eager first call may still be in flight: the capture re-records the events of its fork / join
-        // edges; once per key, so the wait costs nothing in steady state)
+        // (defensive: the capture re-records the events of the fork / join edges the eager first call may still be waiting
+        // on; once per key, so the wait costs nothing in steady state.  The intermittent launch failure first attributed to
+        // this turned out to be the third epilogue team of the halo kernel: profiles/r02_epilogue_ablation.md)
         HBP_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int i = 0; i < kStreams - 1; ++i) if (m->side[i]) HBP_CUDA(cudaStreamSynchronize(m->side[i]));
         HBP_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
